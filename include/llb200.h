@@ -1,0 +1,175 @@
+/*
+ * llb200.h — C ABI of libllb200.so, the B200-native (sm_100a) kernel library behind the LongLive
+ * frame-level autoregressive denoising hot path.
+ *
+ * The reference (kpham-augment/LongLive) has no FFI layer: the hot path is PyTorch library calls
+ * inside wan/modules/causal_model.py.  Each entry point below replaces one group of those calls;
+ * the reference call site it replaces is cited as file:line (relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless noted;
+ *   - bf16 tensors are row-major with explicit leading dimensions given in ELEMENTS;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, is CUDA-graph capturable, and returns 0 on success or a negative LLB_E_*;
+ *     llb_last_error() returns a thread-local description of the last failure;
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry point
+ *     fails with LLB_E_CUDA.
+ */
+#ifndef LLB200_H_
+#define LLB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLB_VERSION 100
+
+#define LLB_OK 0
+#define LLB_E_INVALID (-1) /* bad argument (shape / alignment / null pointer)          */
+#define LLB_E_CUDA (-2)    /* a CUDA runtime / driver call failed                      */
+#define LLB_E_UNSUPPORTED (-3)
+
+int llb_version(void);
+const char* llb_last_error(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t llb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * KV ring-buffer index math (host, integer only).
+ * Replaces the cache bookkeeping of CausalWanSelfAttention.forward
+ * (wan/modules/causal_model.py:206-246, 291-306, 331-360) and CausalWanModel._apply_cache_updates
+ * (:849-905).  All quantities are in tokens.  The reference keeps the window in chronological
+ * order by memmove-ing it ("roll"); here the rolling region is a ring: logical position p >= sink
+ * lives at physical row  sink + (p - sink + rot) % (size - sink), so eviction is `rot += evicted`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct llb_kv_state {
+  int64_t global_end; /* kv_cache["global_end_index"]                      */
+  int64_t local_end;  /* kv_cache["local_end_index"]                       */
+  int64_t rot;        /* ring rotation of the rolling region, in tokens    */
+} llb_kv_state;
+
+typedef struct llb_kv_config {
+  int64_t cache_size;         /* kv_cache["k"].shape[1]                              */
+  int64_t sink_tokens;        /* sink_size * frame_seqlen                            */
+  int64_t max_attention_size; /* CausalWanSelfAttention.max_attention_size           */
+  int32_t local_attn_size;    /* -1 = global attention (never rolls)                 */
+} llb_kv_config;
+
+#define LLB_MAX_SEGS 4
+typedef struct llb_kv_plan {
+  /* reference-observable values (bit-exact contract) */
+  int32_t action; /* 0 = direct_insert, 1 = roll_and_insert */
+  int32_t is_recompute;
+  int64_t current_end;
+  int64_t num_evicted, num_rolled;
+  int64_t local_start, local_end; /* Ls', Le' */
+  int64_t write_start, write_end; /* ws, Le' (logical) */
+  int64_t roped_offset, write_len;
+  int64_t attn_sink_len;     /* logical [0, attn_sink_len) attended                 */
+  int64_t attn_window_start; /* logical [attn_window_start, local_end) attended     */
+  /* physical plan for the kernels */
+  int64_t rot_after; /* ring rotation to use for this call's writes / reads */
+  int32_t n_write_segs;
+  int64_t write_src[LLB_MAX_SEGS], write_dst[LLB_MAX_SEGS], write_n[LLB_MAX_SEGS]; /* new[src..] -> physical rows [dst..] */
+  int32_t n_attn_segs;
+  int64_t attn_start[LLB_MAX_SEGS], attn_len[LLB_MAX_SEGS]; /* physical key-row ranges */
+  int64_t attn_total;
+} llb_kv_plan;
+
+/* Computes the plan for one model forward with `num_new` tokens starting at `current_start`.
+ * Does not modify *st. */
+int llb_kv_ring_plan(const llb_kv_config* cfg, const llb_kv_state* st, int64_t current_start,
+                     int64_t num_new, int32_t sink_recache_after_switch, llb_kv_plan* plan);
+/* Commits the plan after all layers ran (the reference's _apply_cache_updates index update). */
+int llb_kv_ring_commit(const llb_kv_plan* plan, llb_kv_state* st);
+/* physical row of logical position p */
+int64_t llb_kv_ring_phys(const llb_kv_config* cfg, int64_t rot, int64_t p);
+
+/* Per-forward dynamic parameters, resident in DEVICE memory so that one captured CUDA graph
+ * serves every chunk: the host rewrites this struct (one small H2D copy) before each replay. */
+typedef struct llb_step_params {
+  int32_t rope_start_frame; /* current_start // frame_seqlen                                  */
+  int32_t n_write_segs;
+  int32_t write_src[LLB_MAX_SEGS], write_dst[LLB_MAX_SEGS], write_n[LLB_MAX_SEGS];
+  int32_t n_attn_segs;
+  int32_t attn_start[LLB_MAX_SEGS], attn_len[LLB_MAX_SEGS];
+  int32_t reserved[1];
+} llb_step_params;
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM family: out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N]); bf16 in/out, fp32 accumulate
+ * in TMEM (tcgen05.mma, TMA-fed).  Replaces nn.Linear at causal_model.py:90-93,122-126,364,
+ * 406-408,492,601-608 and model.py:172-178,193 together with the elementwise ops that follow.
+ * ------------------------------------------------------------------------------------------ */
+#define LLB_EPI_BIAS 0          /* y = acc + b                                               */
+#define LLB_EPI_BIAS_GELU 1     /* gelu_tanh(y)            (ffn.0 + GELU, causal_model.py:407) */
+#define LLB_EPI_BIAS_SILU 2     /* silu(y)                 (time_embedding, :606)            */
+#define LLB_EPI_BIAS_GATE_RES 3 /* res + y * gate[row / rows_per_gate]   (:456, :467-468)    */
+#define LLB_EPI_BIAS_RES 4      /* res + y                 (cross-attn residual, :460)       */
+
+int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                  int M, int N, int K, int epilogue, const void* bias, const void* gate,
+                  int64_t ld_gate, int rows_per_gate, const void* res, int64_t ld_res,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense attention  out = softmax(Q K^T * scale) V  per head (head_dim 128), flash-style with S/P/O
+ * in TMEM.  Replaces attention()/flash_attention() (wan/modules/attention.py:43-197) at
+ * causal_model.py:349-360 (self-attention over sink ++ window, read IN PLACE from the ring) and
+ * model.py:189 (cross-attention over the cached text K/V).
+ *   q   [Lq, n_heads*128] bf16, k/v [kv_rows, n_heads*128] bf16, out [Lq, n_heads*128] bf16.
+ *   The attended keys are the union of physical row ranges listed in seg_dev
+ *   (llb_step_params.n_attn_segs / attn_start / attn_len, device memory).
+ *   max_kv_tiles bounds the grid-independent loop (host upper bound of sum ceil(len/128)).
+ * ------------------------------------------------------------------------------------------ */
+int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                 int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
+                 const llb_step_params* seg_dev, float scale, int variant, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound).
+ * ------------------------------------------------------------------------------------------ */
+/* LayerNorm(eps, no affine) then x*(1+scale)+shift per frame  (causal_model.py:445, 463-464, 507)
+ * or, with ln_w/ln_b non-null and shift/scale null, affine LayerNorm (norm3, :460).
+ * shift/scale: [n_frames, ld_mod] rows selected by row / rows_per_frame. */
+int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
+                    const void* shift, const void* scale, int64_t ld_mod, int rows_per_frame,
+                    const void* ln_w, const void* ln_b, float eps, void* stream);
+
+/* Fused WanRMSNorm(q), WanRMSNorm(k) (model.py:78-86), causal_rope_apply (causal_model.py:32-60)
+ * and the KV-cache insert (:268-269 / :310-311) in one pass over the fused QKV GEMM output.
+ *   qkv [rows, ld_qkv] = q | k | v column blocks of width C = n_heads*128.
+ *   q_out [rows, ldq] roped queries; k/v written to the ring rows given by p_dev->write_*.
+ *   rope_cs: float2 [1024][64] (cos, sin) table; token -> (frame, h, w) row-major over
+ *   (frames, grid_h, grid_w).  k_cache/v_cache may be null (norm + rope only). */
+int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_out, int64_t ldq,
+                            void* k_cache, void* v_cache, int64_t ld_cache, int rows, int n_heads,
+                            const void* wq, const void* wk, float eps, const void* rope_cs,
+                            int grid_h, int grid_w, const llb_step_params* p_dev, void* stream);
+
+/* Plain WanRMSNorm over C channels: out = bf16(x * rsqrt(mean(x^2)+eps)) * w  (model.py:78-86). */
+int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
+                const void* w, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small glue kernels of CausalWanModel._forward_inference.
+ * ------------------------------------------------------------------------------------------ */
+/* patch_embedding Conv3d(k=s=(1,2,2)) as a gather: x [C_in, F, H, W] -> A [F*(H/2)*(W/2), C_in*4]
+ * (causal_model.py:599-600, 959-963). */
+int llb_patchify(const void* x, void* out, int c_in, int frames, int H, int W, void* stream);
+/* unpatchify (causal_model.py:1240-1263): y [F*(H/2)*(W/2), 4*C_out] -> out [C_out, F, H, W]. */
+int llb_unpatchify(const void* y, void* out, int c_out, int frames, int H, int W, void* stream);
+/* sinusoidal_embedding_1d in fp64 -> bf16 (model.py:15-25): t [n] f32 -> out [n, dim] bf16 */
+int llb_sinusoidal(const float* t, void* out, int n, int dim, void* stream);
+/* out[l, r, :] = bf16(table[l, r % table_rows, :] + e[r, :]) — the per-layer adaLN table
+ * e = modulation + e0 (causal_model.py:440, 506), all layers in one launch. */
+int llb_modulation_table(const void* modulation, const void* e0, void* out, int n_layers,
+                         int n_frames, int width, void* stream);
+int llb_silu(const void* x, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLB200_H_ */

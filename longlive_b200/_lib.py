@@ -1,0 +1,158 @@
+"""ctypes binding of libllb200.so (the C ABI declared in include/llb200.h).
+
+The library is built in-tree (longlive_b200/libllb200.so) by ``__graft_entry__.build()`` or
+``make -C longlive_b200/csrc``.  There is no fallback: if the library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libllb200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+LLB_MAX_SEGS = 4
+
+# epilogues (include/llb200.h)
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES = range(5)
+
+
+class KvState(C.Structure):
+    _fields_ = [("global_end", C.c_int64), ("local_end", C.c_int64), ("rot", C.c_int64)]
+
+
+class KvConfig(C.Structure):
+    _fields_ = [
+        ("cache_size", C.c_int64),
+        ("sink_tokens", C.c_int64),
+        ("max_attention_size", C.c_int64),
+        ("local_attn_size", C.c_int32),
+    ]
+
+
+class KvPlan(C.Structure):
+    _fields_ = [
+        ("action", C.c_int32),
+        ("is_recompute", C.c_int32),
+        ("current_end", C.c_int64),
+        ("num_evicted", C.c_int64),
+        ("num_rolled", C.c_int64),
+        ("local_start", C.c_int64),
+        ("local_end", C.c_int64),
+        ("write_start", C.c_int64),
+        ("write_end", C.c_int64),
+        ("roped_offset", C.c_int64),
+        ("write_len", C.c_int64),
+        ("attn_sink_len", C.c_int64),
+        ("attn_window_start", C.c_int64),
+        ("rot_after", C.c_int64),
+        ("n_write_segs", C.c_int32),
+        ("write_src", C.c_int64 * LLB_MAX_SEGS),
+        ("write_dst", C.c_int64 * LLB_MAX_SEGS),
+        ("write_n", C.c_int64 * LLB_MAX_SEGS),
+        ("n_attn_segs", C.c_int32),
+        ("attn_start", C.c_int64 * LLB_MAX_SEGS),
+        ("attn_len", C.c_int64 * LLB_MAX_SEGS),
+        ("attn_total", C.c_int64),
+    ]
+
+
+class StepParams(C.Structure):
+    """Mirror of llb_step_params (device-resident per-forward parameters), 18 x int32."""
+
+    _fields_ = [
+        ("rope_start_frame", C.c_int32),
+        ("n_write_segs", C.c_int32),
+        ("write_src", C.c_int32 * LLB_MAX_SEGS),
+        ("write_dst", C.c_int32 * LLB_MAX_SEGS),
+        ("write_n", C.c_int32 * LLB_MAX_SEGS),
+        ("n_attn_segs", C.c_int32),
+        ("attn_start", C.c_int32 * LLB_MAX_SEGS),
+        ("attn_len", C.c_int32 * LLB_MAX_SEGS),
+        ("reserved", C.c_int32 * 1),
+    ]
+
+
+STEP_PARAMS_INT32 = C.sizeof(StepParams) // 4
+
+_PROTOS = {
+    # name: (restype, argtypes)
+    "llb_version": (C.c_int, []),
+    "llb_last_error": (C.c_char_p, []),
+    "llb_launch_count": (C.c_int64, []),
+    "llb_kv_ring_plan": (
+        C.c_int,
+        [C.POINTER(KvConfig), C.POINTER(KvState), C.c_int64, C.c_int64, C.c_int32, C.POINTER(KvPlan)],
+    ),
+    "llb_kv_ring_commit": (C.c_int, [C.POINTER(KvPlan), C.POINTER(KvState)]),
+    "llb_kv_ring_phys": (C.c_int64, [C.POINTER(KvConfig), C.c_int64, C.c_int64]),
+    "llb_gemm_bf16": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+         C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
+    ),
+    "llb_attn_fwd": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p],
+    ),
+    "llb_ln_modulate": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+         C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
+    ),
+    "llb_rmsnorm_rope_append": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+         C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+         C.c_void_p],
+    ),
+    "llb_rmsnorm": (
+        C.c_int,
+        [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p],
+    ),
+    "llb_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "llb_unpatchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "llb_sinusoidal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "llb_modulation_table": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "llb_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libllb200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR, "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libllb200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(longlive_b200 has no CPU or PyTorch fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().llb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

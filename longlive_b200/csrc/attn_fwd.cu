@@ -1,0 +1,456 @@
+// llb_attn_fwd — dense flash-style attention for sm_100a (tcgen05 + TMEM + TMA), head_dim 128.
+//
+//   out[Lq, H*128] = softmax(Q K^T * scale) V        per head, bf16 in/out, fp32 S/O in TMEM
+//
+// Replaces flash_attn_varlen_func as reached from wan/modules/attention.py:116-145 for
+//   * self-attention over the rolling KV cache (wan/modules/causal_model.py:331-360): the keys are
+//     "sink ++ local window" of the cache.  The reference clones the cache, memmoves the window
+//     and torch.cat's sink+window before every call; here K/V tiles are TMA-loaded IN PLACE from
+//     the ring buffer: the attended set is a short list of physical row ranges (softmax attention
+//     does not depend on key order), given in device memory so a captured CUDA graph can be
+//     replayed for every chunk;
+//   * cross-attention over the cached 512 text keys (wan/modules/model.py:189).
+//
+// CTA = one head x 256 query rows = two 128-row Q tiles that ping-pong on the tensor core:
+//   warps 0-3   softmax for Q tile 0   (thread == S/O row; TMEM lane quadrant = warp % 4)
+//   warps 4-7   softmax for Q tile 1
+//   warp  8     MMA issuer (one thread): S_t = Q_t K_j^T, O_t += P_t V_j via tcgen05.mma
+//   warp  9     TMA producer: Q tiles once, then K_0,V_0,K_1,V_1,... through a shared-memory ring
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each.  P (bf16) overwrites the first 64
+// columns of its S tile and is consumed straight from TMEM as the A operand of the PV MMA
+// (kPTmem = true); the kPTmem = false variant stages P through swizzled shared memory instead.
+// While the softmax warps of one Q tile work on S_t(j), the tensor core runs the other tile's
+// PV(j-1) and QK(j), so exp2/max/sum overlap with MMA issue.
+// Online softmax uses lazy rescaling: O is only rescaled (in TMEM, by the softmax warps) when the
+// running row max grows by more than 2^8, so the common path never touches O.
+#include "llb_common.cuh"
+#include "llb_host.h"
+
+namespace llb {
+
+constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
+constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
+constexpr int kBoxBytes = 128 * 64 * 2;
+
+template <bool kPTmem>
+struct AttnCfg {
+  static constexpr int kStages = kPTmem ? 5 : 3;
+  static constexpr int kSmemBytes =
+      1024 + 2 * kTileBytes + (kPTmem ? 0 : 2 * kTileBytes) + kStages * kTileBytes + 256;
+};
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  int64_t ldo;
+  int Lq;
+  float scale_log2;
+  const llb_step_params* segs;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Walks the attended key tiles: segments in order, 128-row tiles inside each segment.  Only
+// scalars are kept; the (tiny) segment table is re-read from global memory on a segment switch.
+struct KvTileIter {
+  const llb_step_params* sp;
+  int nseg, seg, off, cur_start, cur_len;
+  __device__ __forceinline__ void load_seg() {
+    cur_len = 0;
+    while (seg < nseg) {
+      cur_start = sp->attn_start[seg];
+      cur_len = sp->attn_len[seg];
+      if (cur_len > 0) break;
+      ++seg;
+    }
+  }
+  __device__ __forceinline__ void init(const llb_step_params* sp_) {
+    sp = sp_;
+    nseg = min(sp->n_attn_segs, LLB_MAX_SEGS);
+    seg = 0;
+    off = 0;
+    cur_start = 0;
+    load_seg();
+  }
+  __device__ __forceinline__ bool done() const { return seg >= nseg; }
+  // current tile: first key row and number of valid keys (1..128)
+  __device__ __forceinline__ void get(int& row0, int& valid) const {
+    row0 = cur_start + off;
+    valid = min(128, cur_len - off);
+  }
+  __device__ __forceinline__ void next() {
+    off += 128;
+    if (off >= cur_len) {
+      off = 0;
+      ++seg;
+      load_seg();
+    }
+  }
+};
+
+template <bool kPTmem>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<kPTmem>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_base = smem_base;                                   // 2 tiles
+  const uint32_t p_base = q_base + 2 * kTileBytes;                     // 2 tiles (smem-P only)
+  const uint32_t kv_base = p_base + (kPTmem ? 0 : 2 * kTileBytes);     // kStages tiles
+  const uint32_t bar_base = kv_base + kStages * kTileBytes;
+  uint8_t* p_gen = smem_gen + 2 * kTileBytes;
+  uint8_t* bar_gen = smem_gen + (bar_base - smem_base);
+  auto qfull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto kvfull_bar = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto kvempty_bar = [&](int s) { return bar_base + 8u * (2 + kStages + s); };
+  auto sfull_bar = [&](int s) { return bar_base + 8u * (2 + 2 * kStages + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (4 + 2 * kStages + s); };
+  auto odone_bar = [&](int s) { return bar_base + 8u * (6 + 2 * kStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * kStages);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (8 + 2 * kStages));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int q_row0 = blockIdx.x * 256;
+  const bool has1 = q_row0 + 128 < p.Lq;  // second Q tile has at least one valid row
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(qfull_bar(s), 1);
+      mbar_init(sfull_bar(s), 1);
+      mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
+      mbar_init(odone_bar(s), 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(kvfull_bar(s), 1);
+      mbar_init(kvempty_bar(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // Register re-distribution: the kernel launches at 168 regs/thread (65536 / 384); the two softmax
+  // warpgroups hold a full 128-column S row per thread and take 216, the MMA/TMA warpgroup keeps 80.
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (warp == 9) {
+    // -------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int col = head * 128;
+      for (int s = 0; s < (has1 ? 2 : 1); ++s) {
+        mbar_arrive_expect_tx(qfull_bar(s), kTileBytes);
+        tma_load_2d(q_base + s * kTileBytes, &tmap_q, qfull_bar(s), col, q_row0 + s * 128);
+        tma_load_2d(q_base + s * kTileBytes + kBoxBytes, &tmap_q, qfull_bar(s), col + 64,
+                    q_row0 + s * 128);
+      }
+      KvTileIter it;
+      it.init(p.segs);
+      int stage = 0;
+      uint32_t phase = 0;
+      while (!it.done()) {
+        int row0, valid;
+        it.get(row0, valid);
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+          mbar_wait(kvempty_bar(stage), phase ^ 1);
+          const uint32_t dst = kv_base + stage * kTileBytes;
+          const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+          mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
+          tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
+          tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        it.next();
+      }
+    }
+  } else if (warp == 8) {
+    // -------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+      auto issue_qk = [&](int t, uint32_t kst) {
+        const uint32_t qa = q_base + t * kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+          umma_ss(tmem_base + t * 128, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o),
+                  idesc_qk, kk != 0);
+        }
+      };
+      auto issue_pv = [&](int t, uint32_t vst, bool first) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA
+          const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
+          const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+          if constexpr (kPTmem) {
+            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bdesc, idesc_pv, acc);
+          } else {
+            const uint32_t pa = p_base + t * kTileBytes + (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+            umma_ss(tmem_base + 256 + t * 128, umma_desc_kmajor(pa), bdesc, idesc_pv, acc);
+          }
+        }
+      };
+      KvTileIter it;
+      it.init(p.segs);
+      int num_tiles = 0;
+      {
+        KvTileIter c = it;
+        while (!c.done()) { ++num_tiles; c.next(); }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
+
+      // prologue: S_t(0) = Q_t K_0^T
+      mbar_wait(qfull_bar(0), 0);
+      mbar_wait(kvfull_bar(stage), phase);
+      tc_fence_after();
+      uint32_t kst = kv_base + stage * kTileBytes;
+      issue_qk(0, kst);
+      umma_commit(sfull_bar(0));
+      if (has1) {
+        mbar_wait(qfull_bar(1), 0);
+        tc_fence_after();
+        issue_qk(1, kst);
+        umma_commit(sfull_bar(1));
+      }
+      umma_commit(kvempty_bar(stage));
+      advance();
+
+      for (int j = 0; j < num_tiles; ++j) {
+        const bool more = j + 1 < num_tiles;
+        // V_j
+        const int vstage = stage;
+        mbar_wait(kvfull_bar(stage), phase);
+        const uint32_t vst = kv_base + stage * kTileBytes;
+        advance();
+        // K_{j+1}
+        int kstage = 0;
+        if (more) {
+          kstage = stage;
+          mbar_wait(kvfull_bar(stage), phase);
+          kst = kv_base + stage * kTileBytes;
+          advance();
+        }
+        // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
+        mbar_wait(pfull_bar(0), j & 1);
+        tc_fence_after();
+        issue_pv(0, vst, j == 0);
+        umma_commit(odone_bar(0));
+        if (more) {
+          issue_qk(0, kst);
+          umma_commit(sfull_bar(0));
+        }
+        if (has1) {
+          mbar_wait(pfull_bar(1), j & 1);
+          tc_fence_after();
+          issue_pv(1, vst, j == 0);
+          umma_commit(odone_bar(1));
+          umma_commit(kvempty_bar(vstage));
+          if (more) {
+            issue_qk(1, kst);
+            umma_commit(sfull_bar(1));
+            umma_commit(kvempty_bar(kstage));
+          }
+        } else {
+          umma_commit(kvempty_bar(vstage));
+          if (more) umma_commit(kvempty_bar(kstage));
+        }
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // -------------------------------------------------------------------- softmax warps
+    const int t = warp >> 2;  // Q tile handled by this warpgroup
+    const int q = warp & 3;   // TMEM lane quadrant
+    if (t == 0 || has1) {
+      const int row_in_tile = q * 32 + lane;
+      const int grow = q_row0 + t * 128 + row_in_tile;
+      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_off + t * 128;
+      const uint32_t t_o = tmem_base + lane_off + 256 + t * 128;
+      const float c = p.scale_log2;
+      float m_used = -INFINITY;
+      float l = 0.f;
+      KvTileIter it;
+      it.init(p.segs);
+      int j = 0;
+      for (; !it.done(); it.next(), ++j) {
+        int row0, valid;
+        it.get(row0, valid);
+        mbar_wait(sfull_bar(t), j & 1);
+        tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
+        tmem_wait_ld();
+        if (valid < 128) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+        }
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        // lazy rescale: only when the max moved by more than 2^8 in the exp2 domain
+        const bool need = (m_new - m_used) * c > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
+          if (j > 0) {
+            // S_t(j) complete implies PV_t(j-1) complete (tensor pipe is in-order), so O is stable
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t ov[32];
+              tmem_ld32(t_o + cc * 32, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+              tmem_st32(t_o + cc * 32, ov);
+            }
+            tmem_wait_st();
+          }
+          l *= f;
+          m_used = m_new;
+        }
+        const float neg = -m_used * c;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * i]), c, neg));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * i + 1]), c, neg));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          if constexpr (kPTmem) {
+            tmem_st16(t_s + cc * 16, pk);
+          } else {
+            // P tile [128 rows x 128 keys], K-major SW128: two 64-key boxes, 16-byte chunks XOR row%8
+            uint8_t* prow = p_gen + t * kTileBytes + (cc >> 1) * kBoxBytes + row_in_tile * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int ch = (cc & 1) * 4 + i;
+              *reinterpret_cast<uint4*>(prow + ((ch ^ (row_in_tile & 7)) << 4)) =
+                  make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
+          }
+        }
+        l += l0 + l1;
+        if constexpr (kPTmem) {
+          tmem_wait_st();
+        } else {
+          fence_proxy_async_smem();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar(t));
+      }
+      // epilogue: O / l -> bf16 -> global
+      mbar_wait(odone_bar(t), (j - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      __nv_bfloat16* orow = p.out + static_cast<int64_t>(grow) * p.ldo + head * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t ov[32];
+        tmem_ld32(t_o + cc * 32, ov);
+        tmem_wait_ld();
+        if (grow < p.Lq) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + cc * 32 + i * 8) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool kPTmem>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, int n_heads, cudaStream_t stream) {
+  using Cfg = AttnCfg<kPTmem>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((p.Lq + 255) / 256, n_heads);
+  attn_fwd_kernel<kPTmem><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  LLB_LAUNCH_CHECK("attn_fwd_kernel");
+  return LLB_OK;
+}
+
+}  // namespace llb
+
+extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
+                            const llb_step_params* seg_dev, float scale, int variant,
+                            void* stream) {
+  using namespace llb;
+  LLB_CHECK_ARG(q && k && v && out && seg_dev, "attn: null tensor");
+  LLB_CHECK_ARG(Lq > 0 && n_heads > 0 && kv_rows > 0, "attn: bad shape");
+  LLB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+                "attn: leading dims must be multiples of 8");
+  LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attn: out must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_2d_bf16(&tq, q, Lq, static_cast<uint64_t>(n_heads) * 128, ldq, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tk, k, kv_rows, static_cast<uint64_t>(n_heads) * 128, ldk, 128, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tv, v, kv_rows, static_cast<uint64_t>(n_heads) * 128, ldv, 128, 64);
+  if (rc) return rc;
+  AttnParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.Lq = Lq;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.segs = seg_dev;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == 1) return launch_attn<false>(tq, tk, tv, p, n_heads, s);
+  return launch_attn<true>(tq, tk, tv, p, n_heads, s);
+}

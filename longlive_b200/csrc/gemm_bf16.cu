@@ -1,0 +1,338 @@
+// llb_gemm_bf16 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias)       A, W, out bf16; fp32 accumulation in TMEM
+//
+// Replaces the nn.Linear calls of the LongLive block (wan/modules/causal_model.py:122-126, 364,
+// 406-408, 492; wan/modules/model.py:172-178, 193) and folds the elementwise tail that follows
+// each of them in the reference into the epilogue:
+//   GELU-tanh (causal_model.py:407), gated residual x + y*e[k] (:456, :467-468), plain residual
+//   (:460), SiLU (:606).  Rounding points mirror the reference (bf16 after the Linear, after the
+//   gate multiply, after the residual add) so the result is bit-comparable to the PyTorch path.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: A tile [128 x 64] and W tile [BN x 64] per k-block into a
+//               kStages-deep shared-memory ring (SWIZZLE_128B), full/empty mbarriers
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into
+//               one of two TMEM accumulator stages; tcgen05.commit frees smem slots / signals
+//               the epilogue
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread == row), add bias, activation,
+//               round to bf16, transpose through a small shared-memory staging buffer so that
+//               global stores (and residual/gate loads) are 128-byte coalesced
+// The two TMEM stages let tile i's epilogue overlap tile i+1's main loop.
+#include "llb_common.cuh"
+#include "llb_host.h"
+
+namespace llb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiStageBytesPerWarp = 32 * 144;  // 32 rows x (128 B + 16 B pad)
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = kBM * kBK * 2;
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes =
+      1024 /*align slack*/ + kStages * kStageBytes + 4 * kEpiStageBytesPerWarp + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int epilogue;
+  __nv_bfloat16* out;
+  int64_t ldo;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* gate;
+  int64_t ld_gate;
+  int rows_per_gate;
+  const __nv_bfloat16* res;
+  int64_t ld_res;
+  int num_m_tiles, num_n_tiles;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // torch.nn.GELU(approximate='tanh'): 0.5*x*(1+tanh(u)), u = sqrt(2/pi)*(x+0.044715*x^3).
+  // 0.5*(1+tanh(u)) == sigmoid(2u): same function, no cancellation in the negative tail, and it
+  // needs one ex2 + one rcp instead of a full-precision tanhf.
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  const float u = kBeta * (x + kKappa * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stage_base = smem_base;
+  const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
+  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = epi_base + 4 * kEpiStageBytesPerWarp;
+  // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(epi_gen + 4 * kEpiStageBytesPerWarp +
+                                           8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = tile % p.num_m_tiles;
+        const int n_idx = tile / p.num_m_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kStageA;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_idx * kBM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n_idx * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = umma_desc_kmajor(sa);
+          const uint64_t db = umma_desc_kmajor(sb);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the
+            // (addr >> 4) field of the descriptor
+            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* my_stage = epi_gen + (warp - 2) * kEpiStageBytesPerWarp;
+    const int epi = p.epilogue;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_idx = tile % p.num_m_tiles;
+      const int n_idx = tile / p.num_m_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = n_idx * BN + c * 64;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(t_row + c * 64, v0);
+        tmem_ld32(t_row + c * 64 + 32, v1);
+        tmem_wait_ld();
+        if (c == BN / 64 - 1) {
+          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        // phase 1: thread == row.  bias (+activation) -> bf16 -> staging row (128 bytes)
+        uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * 144);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint32_t packed[4];
+          // 8 bias values for columns col0 + 8g .. +7 (same address across the warp: broadcast)
+          uint4 bvec = make_uint4(0, 0, 0, 0);
+          if (p.bias != nullptr && col0 + g * 8 < p.N)
+            bvec = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + g * 8));
+          const uint32_t* bb = reinterpret_cast<const uint32_t*>(&bvec);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = g * 8 + e * 2;  // column inside the 64-wide chunk
+            const float a0 = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+            const float a1 = __uint_as_float(j + 1 < 32 ? v0[(j + 1) & 31] : v1[(j + 1) & 31]);
+            float y0 = a0 + bf16_lo(bb[e]), y1 = a1 + bf16_hi(bb[e]);
+            if (epi == LLB_EPI_BIAS_GELU) {
+              y0 = gelu_tanh_f(bf16_round(y0));
+              y1 = gelu_tanh_f(bf16_round(y1));
+            } else if (epi == LLB_EPI_BIAS_SILU) {
+              y0 = silu_f(bf16_round(y0));
+              y1 = silu_f(bf16_round(y1));
+            }
+            packed[e] = pack_bf16x2(y0, y1);
+          }
+          srow[g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncwarp();
+        // phase 2: 8 lanes cover one 128-byte row segment -> coalesced global traffic
+        const int seg = lane & 7;
+        const int gcol = col0 + seg * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          const int grow = m_idx * kBM + q * 32 + r;
+          if (grow < p.M && gcol < p.N) {
+            uint4 y = *reinterpret_cast<const uint4*>(my_stage + r * 144 + seg * 16);
+            if (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES) {
+              const uint4 x =
+                  *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(grow) * p.ld_res + gcol);
+              uint4 gt = make_uint4(0, 0, 0, 0);
+              if (epi == LLB_EPI_BIAS_GATE_RES) {
+                gt = __ldg(reinterpret_cast<const uint4*>(
+                    p.gate + static_cast<int64_t>(grow / p.rows_per_gate) * p.ld_gate + gcol));
+              }
+              const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
+              const uint32_t* xx = reinterpret_cast<const uint32_t*>(&x);
+              const uint32_t* gg = reinterpret_cast<const uint32_t*>(&gt);
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float y0 = bf16_lo(yy[e]), y1 = bf16_hi(yy[e]);
+                if (epi == LLB_EPI_BIAS_GATE_RES) {
+                  y0 = bf16_round(y0 * bf16_lo(gg[e]));
+                  y1 = bf16_round(y1 * bf16_hi(gg[e]));
+                }
+                o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
+              }
+              y = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + gcol) = y;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int sms = device_sm_count();
+  LLB_CHECK_ARG(sms > 0, "no CUDA device");
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  LLB_LAUNCH_CHECK("gemm_bf16_kernel");
+  return LLB_OK;
+}
+
+}  // namespace llb
+
+extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
+                             int64_t ldo, int M, int N, int K, int epilogue, const void* bias,
+                             const void* gate, int64_t ld_gate, int rows_per_gate, const void* res,
+                             int64_t ld_res, void* stream) {
+  using namespace llb;
+  LLB_CHECK_ARG(A && W && out, "gemm: null tensor");
+  LLB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  LLB_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  LLB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: leading dims must be multiples of 8");
+  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_RES, "gemm: unknown epilogue %d", epilogue);
+  if (epilogue == LLB_EPI_BIAS_GATE_RES) {
+    LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
+                  "gemm: gate/residual epilogue needs gate, res, rows_per_gate");
+  }
+  if (epilogue == LLB_EPI_BIAS_RES) LLB_CHECK_ARG(res && ld_res % 8 == 0, "gemm: residual epilogue needs res");
+  LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out must be 16-byte aligned");
+  LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(res) & 15) == 0, "gemm: bias/gate/res must be 16-byte aligned");
+
+  // tile width: 256 when that gives >= ~4 waves-worth of tiles, else 128 / 64 for narrow outputs
+  int bn = 128;
+  if (N <= 64) bn = 64;
+  else if (N >= 4096 && N % 256 == 0) bn = 256;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.epilogue = epilogue;
+  p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.gate = static_cast<const __nv_bfloat16*>(gate); p.ld_gate = ld_gate;
+  p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  p.res = static_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
+  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_n_tiles = (N + bn - 1) / bn;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBM, kBK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, bn, kBK);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_gemm<64>(ta, tb, p, s);
+    case 128: return launch_gemm<128>(ta, tb, p, s);
+    default: return launch_gemm<256>(ta, tb, p, s);
+  }
+}

@@ -1,0 +1,54 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, launch counting,
+// and CUtensorMap encoding through the runtime's driver-entry-point lookup (no libcuda link).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/llb200.h"
+
+namespace llb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define LLB_CHECK_ARG(cond, ...)     \
+  do {                               \
+    if (!(cond)) {                   \
+      llb::set_error(__VA_ARGS__);   \
+      return LLB_E_INVALID;          \
+    }                                \
+  } while (0)
+
+#define LLB_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      llb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                     __LINE__);                                                     \
+      return LLB_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+// Called right after a kernel launch.
+#define LLB_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                 \
+    cudaError_t e_ = cudaGetLastError();                                               \
+    if (e_ != cudaSuccess) {                                                           \
+      llb::set_error("launch of %s failed: %s", name, cudaGetErrorString(e_));         \
+      return LLB_E_CUDA;                                                               \
+    }                                                                                  \
+    llb::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+  } while (0)
+
+// 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements), box
+// [box_rows x box_cols] with 128-byte swizzle (box_cols * 2 bytes must be 128).
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
+int device_sm_count();
+
+}  // namespace llb

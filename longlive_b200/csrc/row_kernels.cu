@@ -1,0 +1,423 @@
+// HBM-bound row kernels of the LongLive block and the small glue kernels of
+// CausalWanModel._forward_inference.  One warp owns one token row (C = 1536 -> six 16-byte vectors
+// per lane), so every global access is a fully coalesced 128-bit transaction and the row statistics
+// are warp-shuffle reductions.  Rounding points follow the reference's bf16 materialisation points
+// (see each kernel) so the outputs are bit-comparable to the PyTorch path.
+#include "llb_common.cuh"
+#include "llb_host.h"
+
+namespace llb {
+
+constexpr int kRowWarps = 8;  // rows per CTA
+constexpr int kMaxVec = 8;    // supports C <= 32 lanes * 8 vecs * 8 elems = 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (+ adaLN modulate)           wan/modules/model.py:89-99, causal_model.py:445,463-464,507
+//   modulate mode:  t = bf16(LN(x)); out = bf16(bf16(t * bf16(1 + scale)) + shift)
+//   affine mode:    out = bf16(LN(x) * w + b)                       (norm3, elementwise_affine)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowWarps * 32)
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+                   int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ shift,
+                   const __nv_bfloat16* __restrict__ scale, int64_t ld_mod, int rows_per_frame,
+                   const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
+                   float eps) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 v[kMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      v[i] = xr[vi];
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s += bf16_lo(w[e]) + bf16_hi(w[e]);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_lo(w[e]) - mean, b = bf16_hi(w[e]) - mean;
+        ss += a * a + b * b;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
+  const bool affine = ln_w != nullptr;
+  const int64_t mrow = static_cast<int64_t>(row / rows_per_frame) * ld_mod;
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+      uint4 a4, b4;
+      if (affine) {
+        a4 = __ldg(reinterpret_cast<const uint4*>(ln_w) + vi);
+        b4 = __ldg(reinterpret_cast<const uint4*>(ln_b) + vi);
+      } else {
+        a4 = __ldg(reinterpret_cast<const uint4*>(scale + mrow) + vi);
+        b4 = __ldg(reinterpret_cast<const uint4*>(shift + mrow) + vi);
+      }
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a4);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b4);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float n0 = (bf16_lo(w[e]) - mean) * rstd, n1 = (bf16_hi(w[e]) - mean) * rstd;
+        float y0, y1;
+        if (affine) {
+          y0 = n0 * bf16_lo(aw[e]) + bf16_lo(bw[e]);
+          y1 = n1 * bf16_hi(aw[e]) + bf16_hi(bw[e]);
+        } else {
+          const float s0 = bf16_round(1.0f + bf16_lo(aw[e])), s1 = bf16_round(1.0f + bf16_hi(aw[e]));
+          y0 = bf16_round(bf16_round(n0) * s0) + bf16_lo(bw[e]);
+          y1 = bf16_round(bf16_round(n1) * s1) + bf16_hi(bw[e]);
+        }
+        o[e] = pack_bf16x2(y0, y1);
+      }
+      orow[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WanRMSNorm row helper (model.py:78-86): y = bf16(bf16(x * rsqrt(mean(x^2) + eps)) * w)
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ float row_sumsq(const uint4 (&v)[NV], int lane, int nvec) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + i * 32 < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_lo(w[e]), b = bf16_hi(w[e]);
+        ss += a * a + b * b;
+      }
+    }
+  }
+  return warp_sum(ss);
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+               int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ wgt, float eps) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 v[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (lane + i * 32 < nvec) v[i] = xr[lane + i * 32];
+  const float rstd = rsqrtf(row_sumsq(v, lane, nvec) / static_cast<float>(C) + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(wgt) + vi);
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(&g4);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = pack_bf16x2(bf16_round(bf16_lo(w[e]) * rstd) * bf16_lo(g[e]),
+                           bf16_round(bf16_hi(w[e]) * rstd) * bf16_hi(g[e]));
+      orow[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused q/k RMSNorm + 3-D RoPE + KV-ring append.
+//   q  = rope(rmsnorm(qkv[:, 0:C]))        -> q_out                    (causal_model.py:122-128, 208-211)
+//   k  = rope(rmsnorm(qkv[:, C:2C]))       -> k_cache[phys(row)]       (:268 / :310)
+//   v  = qkv[:, 2C:3C]                     -> v_cache[phys(row)]       (:269 / :311)
+// RoPE (causal_model.py:32-60): within each 128-wide head, complex pair i = (x[2i], x[2i+1]) is
+// multiplied by exp(i * pos * theta_i) with pos = frame (i < 22), h (22 <= i < 43), w (i >= 43);
+// rope_cs[pos][i] = (cos, sin) as float2, computed in fp64 on the host like the reference's table.
+// The product is evaluated in fp32 (reference: fp64) and rounded to bf16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ring_dst_row(const llb_step_params* sp, int row) {
+  // physical cache row for new-token index `row`, or -1 if this token is not stored
+  const int n = sp->n_write_segs;
+#pragma unroll
+  for (int i = 0; i < LLB_MAX_SEGS; ++i) {
+    if (i < n) {
+      const int src = sp->write_src[i], len = sp->write_n[i];
+      if (row >= src && row < src + len) return sp->write_dst[i] + (row - src);
+    }
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv,
+                           __nv_bfloat16* __restrict__ q_out, int64_t ldq,
+                           __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                           int64_t ld_cache, int rows, int C,
+                           const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                           float eps, const float2* __restrict__ rope_cs, int grid_h, int grid_w,
+                           const llb_step_params* __restrict__ sp) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const int64_t base = static_cast<int64_t>(row) * ld_qkv;
+  const uint4* qr = reinterpret_cast<const uint4*>(qkv + base);
+  const uint4* kr = reinterpret_cast<const uint4*>(qkv + base + C);
+  const uint4* vr = reinterpret_cast<const uint4*>(qkv + base + 2 * C);
+  uint4 qv[kMaxVec], kv[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    if (lane + i * 32 < nvec) {
+      qv[i] = qr[lane + i * 32];
+      kv[i] = kr[lane + i * 32];
+    }
+  }
+  const float q_rstd = rsqrtf(row_sumsq(qv, lane, nvec) / static_cast<float>(C) + eps);
+  const float k_rstd = rsqrtf(row_sumsq(kv, lane, nvec) / static_cast<float>(C) + eps);
+
+  // token -> (frame, h, w), row-major over (frames, grid_h, grid_w)
+  const int hw = grid_h * grid_w;
+  const int f = row / hw, rem = row - f * hw;
+  const int ph = rem / grid_w, pw = rem - ph * grid_w;
+  const int pf = sp->rope_start_frame + f;
+  const int dst = k_cache != nullptr ? ring_dst_row(sp, row) : -1;
+
+  uint4* qo = reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq);
+  uint4* ko = dst >= 0 ? reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
+  uint4* vo = dst >= 0 ? reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      // this vector covers channels [8*vi, 8*vi+8) = complex pairs 4*(vi%16) .. +3 of head vi/16
+      const int pair0 = (vi & 15) * 4;
+      const uint4 wq4 = __ldg(reinterpret_cast<const uint4*>(wq) + vi);
+      const uint4 wk4 = __ldg(reinterpret_cast<const uint4*>(wk) + vi);
+      const uint32_t* qw = reinterpret_cast<const uint32_t*>(&qv[i]);
+      const uint32_t* kw = reinterpret_cast<const uint32_t*>(&kv[i]);
+      const uint32_t* gq = reinterpret_cast<const uint32_t*>(&wq4);
+      const uint32_t* gk = reinterpret_cast<const uint32_t*>(&wk4);
+      uint32_t oq[4], ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int pi = pair0 + e;
+        const int pos = pi < 22 ? pf : (pi < 43 ? ph : pw);
+        const float2 cs = __ldg(rope_cs + pos * 64 + pi);
+        // RMSNorm: bf16(x * rstd) then * weight, rounded to bf16 (model.py:83)
+        const float qa = bf16_round(bf16_round(bf16_lo(qw[e]) * q_rstd) * bf16_lo(gq[e]));
+        const float qb = bf16_round(bf16_round(bf16_hi(qw[e]) * q_rstd) * bf16_hi(gq[e]));
+        const float ka = bf16_round(bf16_round(bf16_lo(kw[e]) * k_rstd) * bf16_lo(gk[e]));
+        const float kb = bf16_round(bf16_round(bf16_hi(kw[e]) * k_rstd) * bf16_hi(gk[e]));
+        oq[e] = pack_bf16x2(qa * cs.x - qb * cs.y, qa * cs.y + qb * cs.x);
+        ok[e] = pack_bf16x2(ka * cs.x - kb * cs.y, ka * cs.y + kb * cs.x);
+      }
+      qo[vi] = make_uint4(oq[0], oq[1], oq[2], oq[3]);
+      if (dst >= 0) {
+        ko[vi] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+        vo[vi] = vr[vi];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// glue kernels
+// ------------------------------------------------------------------------------------------------
+// x [C_in, F, H, W] -> out [F*(H/2)*(W/2), C_in*4]; column = c*4 + ph*2 + pw  (Conv3d weight
+// [1536, C_in, 1, 2, 2].flatten(1) order), row = f*(H/2)*(W/2) + (h/2)*(W/2) + (w/2).
+__global__ void patchify_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                int c_in, int frames, int H, int W) {
+  const int64_t total = static_cast<int64_t>(c_in) * frames * H * W;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int f = (idx / (static_cast<int64_t>(W) * H)) % frames;
+  const int c = idx / (static_cast<int64_t>(W) * H * frames);
+  const int64_t row = (static_cast<int64_t>(f) * (H / 2) + h / 2) * (W / 2) + w / 2;
+  out[row * (c_in * 4) + c * 4 + (h & 1) * 2 + (w & 1)] = x[idx];
+}
+
+// y [F*(H/2)*(W/2), 4*C_out] with column = (ph*2 + pw)*C_out + c  ->  out [C_out, F, H, W]
+// (einsum 'fhwpqrc->cfphqwr', causal_model.py:1259-1261)
+__global__ void unpatchify_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out,
+                                  int c_out, int frames, int H, int W) {
+  const int64_t total = static_cast<int64_t>(c_out) * frames * H * W;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int f = (idx / (static_cast<int64_t>(W) * H)) % frames;
+  const int c = idx / (static_cast<int64_t>(W) * H * frames);
+  const int64_t row = (static_cast<int64_t>(f) * (H / 2) + h / 2) * (W / 2) + w / 2;
+  out[idx] = y[row * (c_out * 4) + ((h & 1) * 2 + (w & 1)) * c_out + c];
+}
+
+// sinusoidal_embedding_1d (model.py:15-25): fp64, cos half first, result cast to bf16.
+__global__ void sinusoidal_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int n,
+                                  int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * dim) return;
+  const int r = idx / dim, c = idx % dim;
+  const int half = dim / 2;
+  const int i = c < half ? c : c - half;
+  const double freq = pow(10000.0, -static_cast<double>(i) / static_cast<double>(half));
+  const double a = static_cast<double>(t[r]) * freq;
+  const double v = c < half ? cos(a) : sin(a);
+  out[idx] = __float2bfloat16_rn(static_cast<float>(v));
+}
+
+// out[l, r, :] = bf16(table[l, r % table_rows, :] + e[r, :])
+__global__ void modulation_table_kernel(const __nv_bfloat16* __restrict__ table,
+                                        const __nv_bfloat16* __restrict__ e,
+                                        __nv_bfloat16* __restrict__ out, int n_layers, int n_frames,
+                                        int width) {
+  const int64_t total = static_cast<int64_t>(n_layers) * n_frames * width;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c = idx % width;
+  const int f = (idx / width) % n_frames;
+  const int l = idx / (static_cast<int64_t>(width) * n_frames);
+  out[idx] = __float2bfloat16_rn(__bfloat162float(table[static_cast<int64_t>(l) * width + c]) +
+                                 __bfloat162float(e[static_cast<int64_t>(f) * width + c]));
+}
+
+__global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                            int64_t n) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const float v = __bfloat162float(x[idx]);
+  out[idx] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
+}
+
+}  // namespace llb
+
+using namespace llb;
+
+extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
+                               const void* shift, const void* scale, int64_t ld_mod,
+                               int rows_per_frame, const void* ln_w, const void* ln_b, float eps,
+                               void* stream) {
+  LLB_CHECK_ARG(x && out && rows > 0, "ln_modulate: null tensor / no rows");
+  LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "ln_modulate: C=%d unsupported", C);
+  LLB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ld_mod % 8 == 0, "ln_modulate: leading dims % 8");
+  const bool affine = ln_w != nullptr;
+  LLB_CHECK_ARG(affine ? (ln_b != nullptr) : (shift && scale && rows_per_frame > 0),
+                "ln_modulate: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;
+  ln_modulate_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
+      static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
+      rows_per_frame > 0 ? rows_per_frame : 1, static_cast<const __nv_bfloat16*>(ln_w),
+      static_cast<const __nv_bfloat16*>(ln_b), eps);
+  LLB_LAUNCH_CHECK("ln_modulate_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
+                           const void* w, float eps, void* stream) {
+  LLB_CHECK_ARG(x && out && w && rows > 0, "rmsnorm: null tensor / no rows");
+  LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "rmsnorm: C=%d unsupported", C);
+  LLB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0, "rmsnorm: leading dims % 8");
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;
+  rmsnorm_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
+      static_cast<const __nv_bfloat16*>(w), eps);
+  LLB_LAUNCH_CHECK("rmsnorm_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_out, int64_t ldq,
+                                       void* k_cache, void* v_cache, int64_t ld_cache, int rows,
+                                       int n_heads, const void* wq, const void* wk, float eps,
+                                       const void* rope_cs, int grid_h, int grid_w,
+                                       const llb_step_params* p_dev, void* stream) {
+  LLB_CHECK_ARG(qkv && q_out && wq && wk && rope_cs && p_dev && rows > 0,
+                "rmsnorm_rope_append: null tensor / no rows");
+  const int C = n_heads * 128;
+  LLB_CHECK_ARG(C <= 32 * kMaxVec * 8, "rmsnorm_rope_append: n_heads=%d unsupported", n_heads);
+  LLB_CHECK_ARG((k_cache == nullptr) == (v_cache == nullptr), "rmsnorm_rope_append: k/v cache mismatch");
+  LLB_CHECK_ARG(ld_qkv % 8 == 0 && ldq % 8 == 0 && ld_cache % 8 == 0 && grid_h > 0 && grid_w > 0,
+                "rmsnorm_rope_append: bad strides / grid");
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;
+  rmsnorm_rope_append_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(q_out), ldq,
+      static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), ld_cache, rows, C,
+      static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), eps,
+      static_cast<const float2*>(rope_cs), grid_h, grid_w, p_dev);
+  LLB_LAUNCH_CHECK("rmsnorm_rope_append_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_patchify(const void* x, void* out, int c_in, int frames, int H, int W,
+                            void* stream) {
+  LLB_CHECK_ARG(x && out && c_in > 0 && frames > 0 && H % 2 == 0 && W % 2 == 0, "patchify: bad args");
+  const int64_t total = static_cast<int64_t>(c_in) * frames * H * W;
+  patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), c_in, frames, H, W);
+  LLB_LAUNCH_CHECK("patchify_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_unpatchify(const void* y, void* out, int c_out, int frames, int H, int W,
+                              void* stream) {
+  LLB_CHECK_ARG(y && out && c_out > 0 && frames > 0 && H % 2 == 0 && W % 2 == 0, "unpatchify: bad args");
+  const int64_t total = static_cast<int64_t>(c_out) * frames * H * W;
+  unpatchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), c_out, frames, H, W);
+  LLB_LAUNCH_CHECK("unpatchify_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_sinusoidal(const float* t, void* out, int n, int dim, void* stream) {
+  LLB_CHECK_ARG(t && out && n > 0 && dim > 0 && dim % 2 == 0, "sinusoidal: bad args");
+  sinusoidal_kernel<<<(n * dim + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, static_cast<__nv_bfloat16*>(out), n, dim);
+  LLB_LAUNCH_CHECK("sinusoidal_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_modulation_table(const void* modulation, const void* e0, void* out, int n_layers,
+                                    int n_frames, int width, void* stream) {
+  LLB_CHECK_ARG(modulation && e0 && out && n_layers > 0 && n_frames > 0 && width > 0,
+                "modulation_table: bad args");
+  const int64_t total = static_cast<int64_t>(n_layers) * n_frames * width;
+  modulation_table_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(modulation), static_cast<const __nv_bfloat16*>(e0),
+      static_cast<__nv_bfloat16*>(out), n_layers, n_frames, width);
+  LLB_LAUNCH_CHECK("modulation_table_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_silu(const void* x, void* out, int64_t n, void* stream) {
+  LLB_CHECK_ARG(x && out && n > 0, "silu: bad args");
+  silu_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), n);
+  LLB_LAUNCH_CHECK("silu_kernel");
+  return LLB_OK;
+}

@@ -1,0 +1,249 @@
+"""Tensor-facing wrappers around the C ABI (include/llb200.h).
+
+PyTorch is used for device memory and streams only: every function takes CUDA bf16 tensors,
+passes raw pointers + strides + the current stream to libllb200.so and returns the output tensor.
+Nothing here computes on the host or falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_SILU,
+                   STEP_PARAMS_INT32, StepParams)
+
+__all__ = [
+    "gemm", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
+    "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
+    "build_rope_table", "launch_count",
+    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.bfloat16) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: longlive_b200 kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise RuntimeError(f"{name}: innermost dimension must be contiguous")
+
+
+def launch_count() -> int:
+    return int(_lib.lib().llb_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+         epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
+         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0,
+         res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  a/w/out 2-D bf16 (row stride arbitrary)."""
+    _req(a, "a"); _req(w, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    assert K == K2, (a.shape, w.shape)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _req(out, "out")
+    for t, n in ((bias, "bias"), (gate, "gate"), (res, "res")):
+        if t is not None:
+            _req(t, n)
+    rc = _lib.lib().llb_gemm_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+        M, N, K, epilogue, _ptr(bias), _ptr(gate), gate.stride(0) if gate is not None else 0,
+        rows_per_gate, _ptr(res), res.stride(0) if res is not None else 0, _stream())
+    _lib.check(rc, "llb_gemm_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def make_step_params(rope_start_frame: int = 0,
+                     writes: Sequence[Tuple[int, int, int]] = (),
+                     attn_segs: Sequence[Tuple[int, int]] = ()) -> StepParams:
+    """writes: (src_row, dst_row, n) triples; attn_segs: (start_row, len) pairs."""
+    sp = StepParams()
+    sp.rope_start_frame = rope_start_frame
+    assert len(writes) <= _lib.LLB_MAX_SEGS and len(attn_segs) <= _lib.LLB_MAX_SEGS
+    sp.n_write_segs = len(writes)
+    for i, (s, d, n) in enumerate(writes):
+        sp.write_src[i], sp.write_dst[i], sp.write_n[i] = s, d, n
+    sp.n_attn_segs = len(attn_segs)
+    for i, (s, n) in enumerate(attn_segs):
+        sp.attn_start[i], sp.attn_len[i] = s, n
+    return sp
+
+
+def step_params_tensor(sp: StepParams, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Uploads a StepParams struct into an int32 device tensor (stream-ordered copy)."""
+    host = torch.frombuffer(bytearray(bytes(sp)), dtype=torch.int32).clone()
+    if out is None:
+        return host.to(device)
+    out.copy_(host, non_blocking=False)
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch.Tensor, *,
+              n_heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
+              variant: int = 0) -> torch.Tensor:
+    """q [Lq, H*128], k/v [rows, H*128] (any row stride), segs_dev: int32 StepParams tensor."""
+    _req(q, "q"); _req(k, "k"); _req(v, "v")
+    assert segs_dev.dtype == torch.int32 and segs_dev.numel() >= STEP_PARAMS_INT32 and segs_dev.is_cuda
+    Lq = q.shape[0]
+    assert q.shape[1] == n_heads * 128 and k.shape[1] == n_heads * 128 and v.shape == k.shape
+    if out is None:
+        out = torch.empty((Lq, n_heads * 128), dtype=torch.bfloat16, device=q.device)
+    if scale is None:
+        scale = 128 ** -0.5
+    rc = _lib.lib().llb_attn_fwd(
+        q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+        out.data_ptr(), out.stride(0), Lq, n_heads, k.shape[0], segs_dev.data_ptr(),
+        C.c_float(scale), variant, _stream())
+    _lib.check(rc, "llb_attn_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def ln_modulate(x: torch.Tensor, *, shift: Optional[torch.Tensor] = None,
+                scale: Optional[torch.Tensor] = None, rows_per_frame: int = 0,
+                ln_w: Optional[torch.Tensor] = None, ln_b: Optional[torch.Tensor] = None,
+                eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x")
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+    ld_mod = 0
+    if shift is not None:
+        _req(shift, "shift"); _req(scale, "scale")
+        assert shift.stride(0) == scale.stride(0)
+        ld_mod = shift.stride(0)
+    rc = _lib.lib().llb_ln_modulate(
+        x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, Cc, _ptr(shift), _ptr(scale),
+        ld_mod, rows_per_frame, _ptr(ln_w), _ptr(ln_b), C.c_float(eps), _stream())
+    _lib.check(rc, "llb_ln_modulate")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x"); _req(w, "w")
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.lib().llb_rmsnorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, Cc,
+                                w.data_ptr(), C.c_float(eps), _stream())
+    _lib.check(rc, "llb_rmsnorm")
+    return out
+
+
+def rmsnorm_rope_append(qkv: torch.Tensor, q_out: torch.Tensor, k_cache: Optional[torch.Tensor],
+                        v_cache: Optional[torch.Tensor], wq: torch.Tensor, wk: torch.Tensor,
+                        rope_cs: torch.Tensor, grid_hw: Tuple[int, int], params_dev: torch.Tensor, *,
+                        n_heads: int, eps: float = 1e-6) -> torch.Tensor:
+    """qkv [rows, 3*H*128]; q_out [rows, H*128]; k_cache/v_cache [cache_rows, H*128]."""
+    _req(qkv, "qkv"); _req(q_out, "q_out")
+    assert rope_cs.dtype == torch.float32 and rope_cs.is_cuda and rope_cs.is_contiguous()
+    rows = qkv.shape[0]
+    ld_cache = 0
+    if k_cache is not None:
+        _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
+        assert k_cache.stride(0) == v_cache.stride(0)
+        ld_cache = k_cache.stride(0)
+    rc = _lib.lib().llb_rmsnorm_rope_append(
+        qkv.data_ptr(), qkv.stride(0), q_out.data_ptr(), q_out.stride(0), _ptr(k_cache), _ptr(v_cache),
+        ld_cache, rows, n_heads, wq.data_ptr(), wk.data_ptr(), C.c_float(eps), rope_cs.data_ptr(),
+        grid_hw[0], grid_hw[1], params_dev.data_ptr(), _stream())
+    _lib.check(rc, "llb_rmsnorm_rope_append")
+    return q_out
+
+
+def patchify(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [C_in, F, H, W] contiguous -> [F*(H/2)*(W/2), 4*C_in]."""
+    _req(x, "x")
+    assert x.is_contiguous()
+    c, f, h, w = x.shape
+    if out is None:
+        out = torch.empty((f * (h // 2) * (w // 2), 4 * c), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.lib().llb_patchify(x.data_ptr(), out.data_ptr(), c, f, h, w, _stream())
+    _lib.check(rc, "llb_patchify")
+    return out
+
+
+def unpatchify(y: torch.Tensor, c_out: int, frames: int, H: int, W: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(y, "y")
+    assert y.is_contiguous() and y.shape == (frames * (H // 2) * (W // 2), 4 * c_out)
+    if out is None:
+        out = torch.empty((c_out, frames, H, W), dtype=torch.bfloat16, device=y.device)
+    rc = _lib.lib().llb_unpatchify(y.data_ptr(), out.data_ptr(), c_out, frames, H, W, _stream())
+    _lib.check(rc, "llb_unpatchify")
+    return out
+
+
+def sinusoidal(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(t, "t", torch.float32)
+    t = t.contiguous().view(-1)
+    if out is None:
+        out = torch.empty((t.numel(), dim), dtype=torch.bfloat16, device=t.device)
+    rc = _lib.lib().llb_sinusoidal(t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream())
+    _lib.check(rc, "llb_sinusoidal")
+    return out
+
+
+def modulation_table(modulation: torch.Tensor, e0: torch.Tensor,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """modulation [n_layers, width], e0 [n_frames, width] -> [n_layers, n_frames, width]."""
+    _req(modulation, "modulation"); _req(e0, "e0")
+    assert modulation.is_contiguous() and e0.is_contiguous()
+    nl, width = modulation.shape
+    nf = e0.shape[0]
+    assert e0.shape[1] == width
+    if out is None:
+        out = torch.empty((nl, nf, width), dtype=torch.bfloat16, device=e0.device)
+    rc = _lib.lib().llb_modulation_table(modulation.data_ptr(), e0.data_ptr(), out.data_ptr(), nl, nf,
+                                         width, _stream())
+    _lib.check(rc, "llb_modulation_table")
+    return out
+
+
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.lib().llb_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "llb_silu")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def build_rope_table(head_dim: int = 128, max_pos: int = 1024, theta: float = 10000.0) -> torch.Tensor:
+    """(cos, sin) table [max_pos, head_dim/2, 2] float32 for the 3-D RoPE of CausalWanModel.
+
+    Same construction as the reference's ``freqs`` (wan/modules/causal_model.py:622-629 with
+    rope_params at wan/modules/model.py:29-36): three frequency groups of head_dim/2 complex pairs,
+    [frame | h | w] = [c - 2*(c//3), c//3, c//3], each group using theta^(-2i/dim_group) with
+    dim_group = d - 4*(d//6), 2*(d//6), 2*(d//6).  Angles are formed in float64.
+    """
+    d = head_dim
+    dims = [d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)]
+    cols = []
+    pos = torch.arange(max_pos, dtype=torch.float64)
+    for dg in dims:
+        inv = 1.0 / torch.pow(torch.tensor(theta, dtype=torch.float64),
+                              torch.arange(0, dg, 2, dtype=torch.float64) / dg)
+        cols.append(torch.outer(pos, inv))
+    ang = torch.cat(cols, dim=1)  # [max_pos, d/2]
+    assert ang.shape[1] == d // 2
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).to(torch.float32).contiguous()
