@@ -148,9 +148,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_gen;
 
   // Register re-distribution: the kernel launches at 168 regs/thread (65536 / 384); the two softmax
-  // warpgroups hold a full 128-column S row per thread and take 216, the MMA/TMA warpgroup keeps 80.
+  // warpgroups hold a full 128-column S row per thread and take 208, the MMA/TMA warpgroup keeps 88
+  // ((168-88)*128 registers released >= (208-168)*256 requested, so the inc never blocks).
   if (warp >= 8) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 9) {
     // -------------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -279,7 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // -------------------------------------------------------------------- softmax warps
     const int t = warp >> 2;  // Q tile handled by this warpgroup
     const int q = warp & 3;   // TMEM lane quadrant

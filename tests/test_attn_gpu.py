@@ -1,0 +1,91 @@
+"""Per-kernel parity of libllb200.so (through the C ABI) against plain fp32 PyTorch references.
+
+These run on the B200 box (`pytest -m gpu`).  Tolerances are stated per test: the kernels round to
+bf16 at the same points as the reference ops, so most comparisons are at bf16 round-off level.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from longlive_b200 import ops
+    return ops
+
+
+def rel_l2(a, b):
+    a = a.float(); b = b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# -------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, H, segs, scale=None):
+    Lq = q.shape[0]
+    idx = torch.cat([torch.arange(s, s + n, device=q.device) for s, n in segs])
+    qh = q.float().view(Lq, H, 128).transpose(0, 1)
+    kh = k.float()[idx].view(-1, H, 128).transpose(0, 1)
+    vh = v.float()[idx].view(-1, H, 128).transpose(0, 1)
+    scale = scale or 128 ** -0.5
+    s = torch.einsum("hqd,hkd->hqk", qh, kh) * scale
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("hqk,hkd->hqd", p, vh)
+    return o.transpose(0, 1).reshape(Lq, H * 128)
+
+
+ATTN_CASES = [
+    # (Lq, H, kv_rows, segs)
+    (128, 1, 128, [(0, 128)]),
+    (256, 2, 256, [(0, 256)]),
+    (200, 2, 300, [(0, 300)]),
+    (4680, 12, 4680, [(0, 4680)]),
+    (4680, 12, 18720, [(0, 18720)]),
+    (4680, 12, 512, [(0, 512)]),
+    (1560, 3, 18720, [(0, 4680), (9360, 3120), (4680, 1000)]),
+    (130, 1, 1000, [(5, 77), (300, 129)]),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["v0", "v1"])
+@pytest.mark.parametrize("Lq,H,rows,segs", ATTN_CASES)
+def test_attention(Lq, H, rows, segs, variant):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(Lq + rows + H)
+    q = bf(torch.randn(Lq, H * 128, generator=g)).to(DEV)
+    k = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    v = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=segs), DEV)
+    out = ops.attention(q, k, v, sp, n_heads=H, variant=variant)
+    ref = _attn_ref(q, k, v, H, segs)
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    # P is rounded to bf16 before the PV product (as in flash-attn): ~3e-3 rel-L2 expected
+    assert err < 8e-3, f"rel-L2 {err}"
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["v0", "v1"])
+def test_attention_large_logits(variant):
+    """Row maxima that grow tile after tile exercise the lazy O-rescale path."""
+    ops = _ops()
+    Lq, H, rows = 256, 1, 2048
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = bf(torch.randn(Lq, 128, generator=g) * 3).to(DEV)
+    k = torch.randn(rows, 128, generator=g)
+    k = bf(k * torch.linspace(0.2, 4.0, rows)[:, None]).to(DEV)  # later keys -> larger logits
+    v = bf(torch.randn(rows, 128, generator=g)).to(DEV)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=[(0, rows)]), DEV)
+    out = ops.attention(q, k, v, sp, n_heads=H, variant=variant)
+    ref = _attn_ref(q, k, v, H, [(0, rows)])
+    err = rel_l2(out, ref)
+    assert err < 1e-2, f"variant {variant}: rel-L2 {err}"
+
+
