@@ -142,6 +142,7 @@ class CausalWanModel(nn.Module):
         self._graphs: Dict[tuple, dict] = {}
         self._param_ring = None
         self._param_slot = 0
+        self.kernel_launches = 0      # libllb200 kernels executed on behalf of this model
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -369,21 +370,29 @@ class CausalWanModel(nn.Module):
         b["t_in"].copy_(t.reshape(-1).to(torch.float32))
 
         if self.use_cuda_graph:
-            gkey = (B, F, H, W, kv_cache[0]["k"].data_ptr(), kv_cache[-1]["v"].data_ptr(),
-                    crossattn_cache[0]["k"].data_ptr(), self.attn_variant)
+            gkey = (B, F, H, W, self.attn_variant,
+                    tuple(c["k"].data_ptr() for c in kv_cache), tuple(c["v"].data_ptr() for c in kv_cache),
+                    tuple(c["k"].data_ptr() for c in crossattn_cache),
+                    tuple(c["v"].data_ptr() for c in crossattn_cache))
             g = self._graphs.get(gkey)
             if g is None:
                 # warm-up run (also sets kernel attributes), then capture
+                n0 = ops.launch_count()
                 self._run_blocks(b, kv_cache, crossattn_cache, B, F, H, W)
+                self.kernel_launches += ops.launch_count() - n0
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
+                n0 = ops.launch_count()
                 with torch.cuda.graph(graph):
                     self._run_blocks(b, kv_cache, crossattn_cache, B, F, H, W)
-                g = {"graph": graph, "launches": 0}
+                g = {"graph": graph, "launches": ops.launch_count() - n0}
                 self._graphs = {gkey: g} if len(self._graphs) > 8 else {**self._graphs, gkey: g}
             g["graph"].replay()
+            self.kernel_launches += g["launches"]
         else:
+            n0 = ops.launch_count()
             self._run_blocks(b, kv_cache, crossattn_cache, B, F, H, W)
+            self.kernel_launches += ops.launch_count() - n0
 
         # --- commit indices (reference: _apply_cache_updates :900-904)
         ring.commit(plan)

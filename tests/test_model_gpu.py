@@ -1,0 +1,150 @@
+"""End-to-end parity of the CUDA path (CausalWanModel + pipelines over libllb200.so) on the B200.
+
+Checkers: (a) fixtures recorded from the REAL reference (tests/golden), (b) the oracle
+(oracle/wan_oracle.py) run on the GPU with the same weights and inputs.
+Gate (BASELINE.json north_star): cache indices / eviction / sink retention bit-exact; denoised
+latents rel-L2 <= 1e-2 per chunk.  `flow_pred` of a random-init 30-layer stack sits at the
+implementation-noise floor of ~7e-3 between any two bf16 implementations, so it
+is reported and only loosely bounded.
+"""
+import os
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _model_from(cfg, sd, use_graph=True):
+    from longlive_b200.model import CausalWanModel
+    m = CausalWanModel(dim=cfg.dim, ffn_dim=cfg.ffn_dim, num_heads=cfg.num_heads, num_layers=cfg.num_layers,
+                       text_dim=cfg.text_dim, text_len=cfg.text_len, local_attn_size=cfg.local_attn_size,
+                       sink_size=cfg.sink_size, frame_seqlen=cfg.frame_seqlen)
+    m.load_state_dict(sd)
+    m = m.to(DEV).to(torch.bfloat16)
+    for mod in m.modules():
+        if hasattr(mod, "max_attention_size"):
+            mod.max_attention_size = cfg.max_attention_size
+    m.use_cuda_graph = use_graph
+    return m
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+def test_small_model_vs_reference_golden(use_graph):
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import SMALL_CFG, small_inputs, small_model_calls
+    from longlive_b200.kv_ring import logical_view
+    gold = torch.load(os.path.join(GOLDEN, "small_model.pt"))
+    cfg = wo.WanConfig(**SMALL_CFG)
+    sd = wo.init_state_dict(cfg, seed=0)
+    model = _model_from(cfg, sd, use_graph)
+    size = cfg.local_attn_size * cfg.frame_seqlen
+    kv = wo.new_kv_cache(cfg, 1, size, DEV)
+    cc = wo.new_crossattn_cache(cfg, 1, DEV)
+    errs = []
+    for i, (start, n, t, kind, pseed) in enumerate(small_model_calls()):
+        if kind == "recache":
+            for c in kv:
+                c["k"].zero_(); c["v"].zero_()
+            for c in cc:
+                c["k"].zero_(); c["v"].zero_(); c["is_init"] = False
+        ctx = wo.synth_prompt_embeds(cfg, pseed, 9).to(DEV)
+        f = model(small_inputs(cfg, i, n).to(DEV), t=torch.full((1, n), t, device=DEV), context=ctx,
+                  kv_cache=kv, crossattn_cache=cc, current_start=start * cfg.frame_seqlen,
+                  sink_recache_after_switch=(kind == "recache"))
+        errs.append(rel_l2(f.cpu(), gold["flows"][i]))
+    print("small-model flow rel-L2 vs reference:", [f"{e:.1e}" for e in errs])
+    assert max(errs) < 1e-2, errs
+    # indices are published with the reference's values
+    assert int(kv[0]["global_end_index"].item()) == gold["global_end"]
+    assert int(kv[-1]["local_end_index"].item()) == gold["local_end"]
+    ring = kv[0]["_llb_ring"]
+    for l in range(cfg.num_layers):
+        k, v = logical_view(kv[l], ring)
+        assert rel_l2(k.cpu(), gold["k"][l]) < 1e-2 and rel_l2(v.cpu(), gold["v"][l]) < 1e-2
+
+
+def _pipe_args(cfg, global_sink=False):
+    class MK(dict):
+        __getattr__ = dict.get
+    return types.SimpleNamespace(
+        denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True, num_frame_per_block=3,
+        context_noise=0, global_sink=global_sink,
+        model_kwargs=MK(local_attn_size=cfg.local_attn_size, sink_size=cfg.sink_size, timestep_shift=5.0))
+
+
+def test_interactive_pipeline_vs_reference_pipeline_golden():
+    """Our InteractiveCausalInferencePipeline on the GPU vs latents produced by the reference's own
+    pipeline + wrapper classes (1-layer 1536-dim model, prompt switch after the first chunk)."""
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import PIPE_CFG, SeededNoise
+    from longlive_b200.pipeline import InteractiveCausalInferencePipeline
+    from longlive_b200.wrapper import WanDiffusionWrapper
+    gold = torch.load(os.path.join(GOLDEN, "pipeline_small.pt"))
+    cfg = wo.WanConfig(**PIPE_CFG)
+    model = _model_from(cfg, wo.init_state_dict(cfg, seed=0))
+    gen = WanDiffusionWrapper(model=model, timestep_shift=5.0)
+    prompts = {"a": wo.synth_prompt_embeds(cfg, 200, 77).to(DEV), "b": wo.synth_prompt_embeds(cfg, 201, 120).to(DEV)}
+    pipe = InteractiveCausalInferencePipeline(
+        _pipe_args(cfg), torch.device(DEV), generator=gen,
+        text_encoder=lambda text_prompts: {"prompt_embeds": prompts[text_prompts[0]]})
+    sn = SeededNoise()
+    pipe.renoise_fn = lambda like, b, s: sn(like)
+    g = torch.Generator().manual_seed(0)
+    noise = torch.randn(1, 6, 16, 60, 104, generator=g).to(torch.bfloat16).to(DEV)
+    _, lat = pipe.inference(noise, text_prompts_list=[["a"], ["b"]], switch_frame_indices=[3],
+                            return_latents=True)
+    errs = [rel_l2(lat[:, 3 * c:3 * c + 3].cpu(), gold["latents"][:, 3 * c:3 * c + 3]) for c in range(2)]
+    print("pipeline latents rel-L2 vs reference pipeline:", errs)
+    assert max(errs) < 1e-2, errs
+    assert int(pipe.kv_cache1[0]["global_end_index"].item()) == gold["global_end"]
+    assert int(pipe.kv_cache1[0]["local_end_index"].item()) == gold["local_end"]
+
+
+def test_full_size_chunks_vs_oracle():
+    """Wan2.1-T2V-1.3B shape (30 blocks), 5 chunks = cache fill + first rolling eviction, 4-step DMD
+    + clean pass per chunk; CUDA pipeline vs the oracle pipeline on the same GPU."""
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import SeededNoise
+    from oracle.pipeline_oracle import run_pipeline
+    from longlive_b200.kv_ring import logical_view
+    from longlive_b200.pipeline import CausalInferencePipeline
+    from longlive_b200.wrapper import WanDiffusionWrapper
+    cfg = wo.WanConfig()
+    sd = wo.init_state_dict(cfg, seed=0)
+    T = 15
+    g = torch.Generator().manual_seed(0)
+    noise = torch.randn(1, T, 16, 60, 104, generator=g).to(torch.bfloat16).to(DEV)
+    prompt = wo.synth_prompt_embeds(cfg, 100, 200).to(DEV)
+    # oracle
+    ogen = wo.OracleGenerator(wo.OracleModel(cfg, sd).to(DEV), shift=5.0)
+    sn = SeededNoise()
+    olat, okv = run_pipeline(ogen, cfg, noise, [prompt], renoise=lambda like, b, s: sn(like))
+    # CUDA path
+    gen = WanDiffusionWrapper(model=_model_from(cfg, sd), timestep_shift=5.0)
+    pipe = CausalInferencePipeline(_pipe_args(cfg), torch.device(DEV), generator=gen,
+                                   text_encoder=lambda text_prompts: {"prompt_embeds": prompt})
+    sn2 = SeededNoise()
+    pipe.renoise_fn = lambda like, b, s: sn2(like)
+    _, lat = pipe.inference(noise, ["p"], return_latents=True)
+    errs = [rel_l2(lat[:, c:c + 3], olat[:, c:c + 3]) for c in range(0, T, 3)]
+    print("full-size latents rel-L2 per chunk vs oracle:", [f"{e:.2e}" for e in errs])
+    assert max(errs) <= 1e-2, errs
+    ring = pipe.kv_cache1[0]["_llb_ring"]
+    assert ring.global_end == int(okv[0]["global_end_index"].item()) == T * 1560
+    assert ring.local_end == int(okv[0]["local_end_index"].item()) == 12 * 1560
+    assert ring.rot == 3 * 1560  # one eviction of one chunk
+    kerr = []
+    for l in (0, 14, 29):
+        k, v = logical_view(pipe.kv_cache1[l], ring)
+        kerr.append((rel_l2(k, okv[l]["k"]), rel_l2(v, okv[l]["v"])))
+    print("cache K/V rel-L2 (layers 0, 14, 29):", kerr)
+    assert max(max(p) for p in kerr) < 3e-2
