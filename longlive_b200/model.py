@@ -200,7 +200,7 @@ class CausalWanModel(nn.Module):
         self._packed = P
         return P
 
-    def _buffers(self, B: int, F: int, H: int, W: int, dev):
+    def _workspace_for(self, B: int, F: int, H: int, W: int, dev):
         key = (B, F, H, W)
         if key not in self._bufs:
             bf = torch.bfloat16
@@ -354,7 +354,7 @@ class CausalWanModel(nn.Module):
         L = F * fs
         assert seq_len is None or L <= seq_len
         assert current_start % fs == 0, "current_start must be frame aligned"
-        b = self._buffers(B, F, H, W, x.device)
+        b = self._workspace_for(B, F, H, W, x.device)
 
         # --- integer bookkeeping (host only; replaces the reference's .item() round trips)
         ring = self._ring_of(kv_cache, fs)
