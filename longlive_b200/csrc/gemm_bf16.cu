@@ -34,8 +34,9 @@ struct GemmCfg {
   static constexpr int kStageA = kBM * kBK * 2;
   static constexpr int kStageB = BN * kBK * 2;
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  // TMEM allocations are powers of two >= 32 columns; two accumulator stages of BN columns each
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSmemBytes =
       1024 /*align slack*/ + kStages * kStageBytes + 4 * kEpiStageBytesPerWarp + 256 /*barriers*/;
 };
@@ -309,10 +310,23 @@ extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(res) & 15) == 0, "gemm: bias/gate/res must be 16-byte aligned");
 
-  // tile width: 256 when that gives >= ~4 waves-worth of tiles, else 128 / 64 for narrow outputs
-  int bn = 128;
-  if (N <= 64) bn = 64;
-  else if (N >= 4096 && N % 256 == 0) bn = 256;
+  // Tile width: minimise (waves over the SMs) x (per-tile MMA time ~ BN), with a penalty for the
+  // narrower tiles whose SS-mode MMAs sit closer to the shared-memory bandwidth limit
+  // (A 4 KB + B BN*32 B per K=16 step of BN/2 cycles: 128 B/clk at BN=128, 107 at 192, 96 at 256).
+  int bn = 64;
+  if (N > 64) {
+    const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+    const int m_tiles = (M + kBM - 1) / kBM;
+    const int cand[3] = {128, 192, 256};
+    const double penalty[3] = {1.15, 1.05, 1.0};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      const int tiles = m_tiles * ((N + cand[i] - 1) / cand[i]);
+      const int waves = (tiles + sms - 1) / sms;
+      const double cost = waves * cand[i] * penalty[i];
+      if (cost < best) { best = cost; bn = cand[i]; }
+    }
+  }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.epilogue = epilogue;
@@ -333,6 +347,7 @@ extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   switch (bn) {
     case 64: return launch_gemm<64>(ta, tb, p, s);
     case 128: return launch_gemm<128>(ta, tb, p, s);
+    case 192: return launch_gemm<192>(ta, tb, p, s);
     default: return launch_gemm<256>(ta, tb, p, s);
   }
 }
