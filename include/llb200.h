@@ -122,11 +122,15 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
  *   q   [Lq, n_heads*128] bf16, k/v [kv_rows, n_heads*128] bf16, out [Lq, n_heads*128] bf16.
  *   The attended keys are the union of physical row ranges listed in seg_dev
  *   (llb_step_params.n_attn_segs / attn_start / attn_len, device memory).
- *   max_kv_tiles bounds the grid-independent loop (host upper bound of sum ceil(len/128)).
  * ------------------------------------------------------------------------------------------ */
 int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                  int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
-                 const llb_step_params* seg_dev, float scale, int variant, void* stream);
+                 const llb_step_params* seg_dev, float scale, int variant, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+/* Size of the device workspace llb_attn_fwd needs (partial O / (m,l) / flags of the stream-K
+ * split, one slice per SM).  Allocate once per device, zero it once, reuse for every launch on
+ * streams that are ordered with respect to each other. */
+int64_t llb_attn_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound).

@@ -96,8 +96,9 @@ _PROTOS = {
     "llb_attn_fwd": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p],
+         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
     ),
+    "llb_attn_workspace_bytes": (C.c_int64, []),
     "llb_ln_modulate": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

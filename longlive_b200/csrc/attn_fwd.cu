@@ -23,14 +23,35 @@
 // PV(j-1) and QK(j), so exp2/max/sum overlap with MMA issue.
 // Online softmax uses lazy rescaling: O is only rescaled (in TMEM, by the softmax warps) when the
 // running row max grows by more than 2^8, so the common path never touches O.
+//
+// Scheduling (persistent; whole-item rounds + split remainder): 12 heads x 19 Q pairs = 228 items
+// do not divide over 148 SMs (1.54 waves).  The grid is one CTA per SM.  Every CTA first processes
+// n_items / G whole items in lockstep rounds (CTAs sharing a head stream the same K/V tiles out of
+// L2 at the same time); the n_items % G left-over items are then cut into equal contiguous ranges
+// of the flattened (item, kv-tile) space, one per CTA.  A part that does not contain kv tile 0
+// writes its un-normalised O (fp32) and (m, l) per row to a workspace and raises a per-row flag;
+// the CTA owning the preceding kv range of the same item (always the previous CTA) waits for it,
+// merges, and either passes the merged partial on or - if it owns kv tile 0 - normalises and
+// writes the output.  The launch is cooperative (all CTAs co-resident: grid <= #SMs, 1 CTA/SM), so the flag wait cannot
+// deadlock; flags are consumed (reset to 0) by their reader, which keeps the kernel replayable
+// inside a CUDA graph.
 #include "llb_common.cuh"
 #include "llb_host.h"
+
+#include <stdlib.h>
 
 namespace llb {
 
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
+constexpr int kMinSplitTiles = 16;  // stream-K only when an item has at least this many kv tiles
+
+// workspace per CTA: partial O [2 tiles][32 col4][128 rows] float4, (m,l) [2][128] float2, flags [2][128]
+constexpr int64_t kWsOBytes = 2ll * 32 * 128 * 16;
+constexpr int64_t kWsMlBytes = 2ll * 128 * 8;
+constexpr int64_t kWsFlagBytes = 2ll * 128 * 4;
+constexpr int64_t kWsPerCta = kWsOBytes + kWsMlBytes + kWsFlagBytes;
 
 template <bool kPTmem>
 struct AttnCfg {
@@ -43,14 +64,34 @@ struct AttnParams {
   __nv_bfloat16* out;
   int64_t ldo;
   int Lq;
+  int n_heads;
+  int n_pairs;  // ceil(Lq / 256)
   float scale_log2;
   const llb_step_params* segs;
+  uint8_t* workspace;  // gridDim.x * kWsPerCta bytes, flags zero-initialised once
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
 }
 
 // Walks the attended key tiles: segments in order, 128-row tiles inside each segment.  Only
@@ -75,7 +116,27 @@ struct KvTileIter {
     cur_start = 0;
     load_seg();
   }
-  __device__ __forceinline__ bool done() const { return seg >= nseg; }
+  __device__ __forceinline__ int total_tiles() const {
+    int n = 0;
+    for (int i = 0; i < nseg; ++i) {
+      const int l = sp->attn_len[i];
+      if (l > 0) n += (l + 127) >> 7;
+    }
+    return n;
+  }
+  // position on kv tile index t (0-based over the whole attended set)
+  __device__ __forceinline__ void seek(int t) {
+    seg = 0;
+    off = 0;
+    load_seg();
+    while (seg < nseg) {
+      const int nt = (cur_len + 127) >> 7;
+      if (t < nt) { off = t << 7; return; }
+      t -= nt;
+      ++seg;
+      load_seg();
+    }
+  }
   // current tile: first key row and number of valid keys (1..128)
   __device__ __forceinline__ void get(int& row0, int& valid) const {
     row0 = cur_start + off;
@@ -88,6 +149,62 @@ struct KvTileIter {
       ++seg;
       load_seg();
     }
+  }
+};
+
+// Per-CTA list of work segments (item, kv tiles [t0, t1)).
+//   rounds:    items k*G + c for k < n_items / G are processed whole; all CTAs walk the kv tiles in
+//              lockstep, so CTAs that share a head hit the same K/V tiles in L2 at the same time
+//   remainder: the last n_items % G items are cut into equal contiguous ranges of the flattened
+//              (item, kv tile) space, one range per CTA (at most kMaxParts parts per item); parts of
+//              one item live in consecutive CTAs and are merged head <- ... <- tail through the workspace
+constexpr int kMaxParts = 4;
+struct SegIter {
+  int T, G, c, rounds, rem_items, k;
+  bool split;
+  int ru, ru_end;
+  int item, t0, t1;
+  bool ok;
+  __device__ __forceinline__ void init(int T_, int n_items, int G_, int c_) {
+    T = T_; G = G_; c = c_;
+    rounds = n_items / G;
+    rem_items = n_items - rounds * G;
+    k = 0;
+    split = (T >= kMinSplitTiles) && rem_items > 0;
+    ru = ru_end = 0;
+    if (split) {
+      const int gp = min(G, rem_items * kMaxParts);  // CTAs that take part in the remainder
+      if (c < gp) {
+        const long long R = static_cast<long long>(rem_items) * T;
+        ru = static_cast<int>(R * c / gp);
+        ru_end = static_cast<int>(R * (c + 1) / gp);
+      }
+    }
+    load();
+  }
+  __device__ __forceinline__ void load() {
+    ok = false;
+    if (T <= 0) return;
+    if (k < rounds) {
+      item = k * G + c; t0 = 0; t1 = T; ok = true;
+    } else if (split) {
+      if (ru < ru_end) {
+        const int ri = ru / T;
+        item = rounds * G + ri;
+        t0 = ru - ri * T;
+        const int rem = ru_end - ru;
+        t1 = (rem < T - t0) ? t0 + rem : T;
+        ok = true;
+      }
+    } else if (k == rounds && c < rem_items) {
+      item = rounds * G + c; t0 = 0; t1 = T; ok = true;
+    }
+  }
+  __device__ __forceinline__ bool in_remainder() const { return k >= rounds && split; }
+  __device__ __forceinline__ void next() {
+    if (k < rounds || !split) ++k;
+    else ru += t1 - t0;
+    load();
   }
 };
 
@@ -107,20 +224,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* p_gen = smem_gen + 2 * kTileBytes;
   uint8_t* bar_gen = smem_gen + (bar_base - smem_base);
   auto qfull_bar = [&](int s) { return bar_base + 8u * s; };
-  auto kvfull_bar = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto kvempty_bar = [&](int s) { return bar_base + 8u * (2 + kStages + s); };
-  auto sfull_bar = [&](int s) { return bar_base + 8u * (2 + 2 * kStages + s); };
-  auto pfull_bar = [&](int s) { return bar_base + 8u * (4 + 2 * kStages + s); };
-  auto odone_bar = [&](int s) { return bar_base + 8u * (6 + 2 * kStages + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * kStages);
+  auto qempty_bar = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto sfull_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto odone_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto ofree_bar = [&](int s) { return bar_base + 8u * (10 + s); };
+  auto kvfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (12 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (8 + 2 * kStages));
+      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (12 + 2 * kStages));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int q_row0 = blockIdx.x * 256;
-  const bool has1 = q_row0 + 128 < p.Lq;  // second Q tile has at least one valid row
 
   if (warp == 9 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -128,9 +244,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_v);
     for (int s = 0; s < 2; ++s) {
       mbar_init(qfull_bar(s), 1);
+      mbar_init(qempty_bar(s), 1);
       mbar_init(sfull_bar(s), 1);
       mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
+      mbar_init(ofree_bar(s), 4);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
@@ -147,159 +265,218 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  // work decomposition: identical in every role, evaluated inside each role branch so that only
+  // the state a role needs stays live under its register budget
+#define LLB_ATTN_INIT_WORK()                                            \
+  KvTileIter kv_it;                                                     \
+  kv_it.init(p.segs);                                                   \
+  SegIter sg;                                                           \
+  sg.init(kv_it.total_tiles(), p.n_heads * p.n_pairs, gridDim.x, blockIdx.x)
+
   // Register re-distribution: the kernel launches at 168 regs/thread (65536 / 384); the two softmax
   // warpgroups hold a full 128-column S row per thread and take 208, the MMA/TMA warpgroup keeps 88
   // ((168-88)*128 registers released >= (208-168)*256 requested, so the inc never blocks).
   if (warp >= 8) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-  if (warp == 9) {
-    // -------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      const int col = head * 128;
-      for (int s = 0; s < (has1 ? 2 : 1); ++s) {
-        mbar_arrive_expect_tx(qfull_bar(s), kTileBytes);
-        tma_load_2d(q_base + s * kTileBytes, &tmap_q, qfull_bar(s), col, q_row0 + s * 128);
-        tma_load_2d(q_base + s * kTileBytes + kBoxBytes, &tmap_q, qfull_bar(s), col + 64,
-                    q_row0 + s * 128);
-      }
-      KvTileIter it;
-      it.init(p.segs);
-      int stage = 0;
-      uint32_t phase = 0;
-      while (!it.done()) {
-        int row0, valid;
-        it.get(row0, valid);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 9) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+        LLB_ATTN_INIT_WORK();
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t qph0 = 0, qph1 = 0;
+        for (; sg.ok; sg.next()) {
+          const int head = sg.item / p.n_pairs;
+          const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+          const bool has1 = q_row0 + 128 < p.Lq;
+          const int col = head * 128;
+          // Q tiles: wait until the MMA warp has issued the previous segment's last QK on this slot
+          mbar_wait(qempty_bar(0), qph0 ^ 1);
+          qph0 ^= 1;
+          mbar_arrive_expect_tx(qfull_bar(0), kTileBytes);
+          tma_load_2d(q_base, &tmap_q, qfull_bar(0), col, q_row0);
+          tma_load_2d(q_base + kBoxBytes, &tmap_q, qfull_bar(0), col + 64, q_row0);
+          if (has1) {
+            mbar_wait(qempty_bar(1), qph1 ^ 1);
+            qph1 ^= 1;
+            mbar_arrive_expect_tx(qfull_bar(1), kTileBytes);
+            tma_load_2d(q_base + kTileBytes, &tmap_q, qfull_bar(1), col, q_row0 + 128);
+            tma_load_2d(q_base + kTileBytes + kBoxBytes, &tmap_q, qfull_bar(1), col + 64, q_row0 + 128);
+          }
+          kv_it.seek(sg.t0);
+          for (int j = sg.t0; j < sg.t1; ++j) {
+            int row0, valid;
+            kv_it.get(row0, valid);
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          mbar_wait(kvempty_bar(stage), phase ^ 1);
-          const uint32_t dst = kv_base + stage * kTileBytes;
-          const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
-          mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
-          tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
-          tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        it.next();
-      }
-    }
-  } else if (warp == 8) {
-    // -------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
-      auto issue_qk = [&](int t, uint32_t kst) {
-        const uint32_t qa = q_base + t * kTileBytes;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          umma_ss(tmem_base + t * 128, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o),
-                  idesc_qk, kk != 0);
-        }
-      };
-      auto issue_pv = [&](int t, uint32_t vst, bool first) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA
-          const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
-          const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-          if constexpr (kPTmem) {
-            umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bdesc, idesc_pv, acc);
-          } else {
-            const uint32_t pa = p_base + t * kTileBytes + (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-            umma_ss(tmem_base + 256 + t * 128, umma_desc_kmajor(pa), bdesc, idesc_pv, acc);
+            for (int kv = 0; kv < 2; ++kv) {
+              mbar_wait(kvempty_bar(stage), phase ^ 1);
+              const uint32_t dst = kv_base + stage * kTileBytes;
+              const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+              mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
+              tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
+              tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            kv_it.next();
           }
         }
-      };
-      KvTileIter it;
-      it.init(p.segs);
-      int num_tiles = 0;
+      }
+    } else if (warp == 8) {
+      // ------------------------------------------------------------------ MMA issuer
+      // The whole warp runs this loop (waits included); one elected lane issues the tcgen05 ops.
       {
-        KvTileIter c = it;
-        while (!c.done()) { ++num_tiles; c.next(); }
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
-
-      // prologue: S_t(0) = Q_t K_0^T
-      mbar_wait(qfull_bar(0), 0);
-      mbar_wait(kvfull_bar(stage), phase);
-      tc_fence_after();
-      uint32_t kst = kv_base + stage * kTileBytes;
-      issue_qk(0, kst);
-      umma_commit(sfull_bar(0));
-      if (has1) {
-        mbar_wait(qfull_bar(1), 0);
-        tc_fence_after();
-        issue_qk(1, kst);
-        umma_commit(sfull_bar(1));
-      }
-      umma_commit(kvempty_bar(stage));
-      advance();
-
-      for (int j = 0; j < num_tiles; ++j) {
-        const bool more = j + 1 < num_tiles;
-        // V_j
-        const int vstage = stage;
-        mbar_wait(kvfull_bar(stage), phase);
-        const uint32_t vst = kv_base + stage * kTileBytes;
-        advance();
-        // K_{j+1}
-        int kstage = 0;
-        if (more) {
-          kstage = stage;
-          mbar_wait(kvfull_bar(stage), phase);
-          kst = kv_base + stage * kTileBytes;
-          advance();
-        }
-        // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
-        mbar_wait(pfull_bar(0), j & 1);
-        tc_fence_after();
-        issue_pv(0, vst, j == 0);
-        umma_commit(odone_bar(0));
-        if (more) {
-          issue_qk(0, kst);
-          umma_commit(sfull_bar(0));
-        }
-        if (has1) {
-          mbar_wait(pfull_bar(1), j & 1);
-          tc_fence_after();
-          issue_pv(1, vst, j == 0);
-          umma_commit(odone_bar(1));
-          umma_commit(kvempty_bar(vstage));
-          if (more) {
-            issue_qk(1, kst);
-            umma_commit(sfull_bar(1));
-            umma_commit(kvempty_bar(kstage));
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+        auto issue_qk = [&](int t, uint32_t kst) {
+          const uint32_t qa = q_base + t * kTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+            umma_ss(tmem_base + t * 128, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o),
+                    idesc_qk, kk != 0);
           }
-        } else {
-          umma_commit(kvempty_bar(vstage));
-          if (more) umma_commit(kvempty_bar(kstage));
+        };
+        auto issue_pv = [&](int t, uint32_t vst, bool first) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA
+            const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
+            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+            if constexpr (kPTmem) {
+              umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bdesc, idesc_pv, acc);
+            } else {
+              const uint32_t pa = p_base + t * kTileBytes + (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+              umma_ss(tmem_base + 256 + t * 128, umma_desc_kmajor(pa), bdesc, idesc_pv, acc);
+            }
+          }
+        };
+        LLB_ATTN_INIT_WORK();
+        int stage = 0;
+        uint32_t phase = 0;
+        auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
+        uint32_t qph0 = 0, qph1 = 0;    // q_full consumer phases
+        uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
+        uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
+
+        for (; sg.ok; sg.next()) {
+          const int head = sg.item / p.n_pairs;
+          const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+          const bool has1 = q_row0 + 128 < p.Lq;
+          const int nt = sg.t1 - sg.t0;
+          // prologue: S_t(first) = Q_t K^T
+          mbar_wait(qfull_bar(0), qph0);
+          qph0 ^= 1;
+          if (has1) {
+            mbar_wait(qfull_bar(1), qph1);
+            qph1 ^= 1;
+          }
+          mbar_wait(kvfull_bar(stage), phase);
+          tc_fence_after();
+          uint32_t kst = kv_base + stage * kTileBytes;
+          if (elect_one()) {
+            issue_qk(0, kst);
+            umma_commit(sfull_bar(0));
+            if (nt == 1) umma_commit(qempty_bar(0));
+            if (has1) {
+              issue_qk(1, kst);
+              umma_commit(sfull_bar(1));
+              if (nt == 1) umma_commit(qempty_bar(1));
+            }
+            umma_commit(kvempty_bar(stage));
+          }
+          __syncwarp();
+          advance();
+          // O_t of the previous segment must have been drained by its softmax warps before the
+          // first PV of this segment overwrites it
+          mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
+          oseg0++;
+          if (has1) {
+            mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
+            oseg1++;
+          }
+          for (int j = 0; j < nt; ++j) {
+            const bool more = j + 1 < nt;
+            const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
+            // V_j
+            const int vstage = stage;
+            mbar_wait(kvfull_bar(stage), phase);
+            const uint32_t vst = kv_base + stage * kTileBytes;
+            advance();
+            // K_{j+1}
+            int kstage = 0;
+            if (more) {
+              kstage = stage;
+              mbar_wait(kvfull_bar(stage), phase);
+              kst = kv_base + stage * kTileBytes;
+              advance();
+            }
+            // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
+            mbar_wait(pfull_bar(0), pcnt0 & 1);
+            pcnt0++;
+            tc_fence_after();
+            if (elect_one()) {
+              issue_pv(0, vst, j == 0);
+              umma_commit(odone_bar(0));
+              if (more) {
+                issue_qk(0, kst);
+                umma_commit(sfull_bar(0));
+                if (last_qk) umma_commit(qempty_bar(0));
+              }
+              if (!has1) {
+                umma_commit(kvempty_bar(vstage));
+                if (more) umma_commit(kvempty_bar(kstage));
+              }
+            }
+            __syncwarp();
+            if (has1) {
+              mbar_wait(pfull_bar(1), pcnt1 & 1);
+              pcnt1++;
+              tc_fence_after();
+              if (elect_one()) {
+                issue_pv(1, vst, j == 0);
+                umma_commit(odone_bar(1));
+                umma_commit(kvempty_bar(vstage));
+                if (more) {
+                  issue_qk(1, kst);
+                  umma_commit(sfull_bar(1));
+                  if (last_qk) umma_commit(qempty_bar(1));
+                  umma_commit(kvempty_bar(kstage));
+                }
+              }
+              __syncwarp();
+            }
+          }
         }
       }
     }
-  }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // -------------------------------------------------------------------- softmax warps
     const int t = warp >> 2;  // Q tile handled by this warpgroup
     const int q = warp & 3;   // TMEM lane quadrant
-    if (t == 0 || has1) {
-      const int row_in_tile = q * 32 + lane;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + t * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + t * 128;
+    const float c = p.scale_log2;
+    uint32_t cnt = 0;  // kv tiles processed by this warpgroup (s_full / o_done phase)
+    const int64_t ws_row = static_cast<int64_t>(t) * 128 + row_in_tile;
+    LLB_ATTN_INIT_WORK();
+
+    for (; sg.ok; sg.next()) {
+      const int head = sg.item / p.n_pairs;
+      const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+      const bool has1 = q_row0 + 128 < p.Lq;
+      if (t == 1 && !has1) continue;
       const int grow = q_row0 + t * 128 + row_in_tile;
-      const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-      const uint32_t t_s = tmem_base + lane_off + t * 128;
-      const uint32_t t_o = tmem_base + lane_off + 256 + t * 128;
-      const float c = p.scale_log2;
       float m_used = -INFINITY;
       float l = 0.f;
-      KvTileIter it;
-      it.init(p.segs);
-      int j = 0;
-      for (; !it.done(); it.next(), ++j) {
+      kv_it.seek(sg.t0);
+      for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
         int row0, valid;
-        it.get(row0, valid);
-        mbar_wait(sfull_bar(t), j & 1);
+        kv_it.get(row0, valid);
+        mbar_wait(sfull_bar(t), cnt & 1);
+        cnt++;
         tc_fence_after();
         uint32_t sv[4][32];
 #pragma unroll
@@ -325,7 +502,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const bool need = (m_new - m_used) * c > 8.0f;
         if (__any_sync(0xffffffffu, need)) {
           const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
-          if (j > 0) {
+          if (j > sg.t0) {
             // S_t(j) complete implies PV_t(j-1) complete (tensor pipe is in-order), so O is stable
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -377,28 +554,91 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull_bar(t));
       }
-      // epilogue: O / l -> bf16 -> global
-      mbar_wait(odone_bar(t), (j - 1) & 1);
+      // ---- segment epilogue
+      mbar_wait(odone_bar(t), (cnt - 1) & 1);
       tc_fence_after();
-      const float inv = 1.0f / l;
+      const bool tail_part = sg.in_remainder() && sg.t0 > 0;     // earlier kv tiles live in CTA blockIdx.x - 1
+      const bool head_part = sg.in_remainder() && sg.t1 < sg.T;  // later kv tiles live in CTA blockIdx.x + 1
+      const bool row_ok = grow < p.Lq;
+      float a_own = 1.0f, a_oth = 0.0f;
+      const float4* wo_in = nullptr;
+      uint32_t* flag_in = nullptr;
+      if (head_part && row_ok) {
+        // wait for the partial (O, m, l) of the later kv tiles of this item
+        uint8_t* wsb = p.workspace + static_cast<int64_t>(blockIdx.x + 1) * kWsPerCta;
+        flag_in = reinterpret_cast<uint32_t*>(wsb + kWsOBytes + kWsMlBytes) + ws_row;
+        uint32_t spins = 0;
+        uint64_t t_start = 0;
+        while (ld_acquire_u32(flag_in) == 0u) {
+          if ((++spins & 0xfffu) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > LLB_WAIT_TIMEOUT_NS) __trap();
+          }
+        }
+        const volatile float* mlp = reinterpret_cast<const volatile float*>(wsb + kWsOBytes) + 2 * ws_row;
+        const float m_oth = mlp[0], l_oth = mlp[1];
+        const float m = fmaxf(m_used, m_oth);
+        a_own = ex2_approx((m_used - m) * c);
+        a_oth = ex2_approx((m_oth - m) * c);
+        l = l * a_own + l_oth * a_oth;
+        m_used = m;
+        wo_in = reinterpret_cast<const float4*>(wsb) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
+      }
+      uint8_t* wsb_out = p.workspace + static_cast<int64_t>(blockIdx.x) * kWsPerCta;
+      float4* wo_out = reinterpret_cast<float4*>(wsb_out) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
+      if (!tail_part) {  // this CTA owns kv tile 0 of the item: normalise and write the output
+        const float inv = 1.0f / l;
+        a_own *= inv;
+        a_oth *= inv;
+      }
       __nv_bfloat16* orow = p.out + static_cast<int64_t>(grow) * p.ldo + head * 128;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t ov[32];
         tmem_ld32(t_o + cc * 32, ov);
         tmem_wait_ld();
-        if (grow < p.Lq) {
+        if (row_ok) {
+          float o[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + cc * 32 + i * 8) = w;
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(ov[i]) * a_own;
+          if (wo_in != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 x = ld_cg_f4(wo_in + (cc * 8 + i) * 128);
+              o[4 * i] += x.x * a_oth;
+              o[4 * i + 1] += x.y * a_oth;
+              o[4 * i + 2] += x.z * a_oth;
+              o[4 * i + 3] += x.w * a_oth;
+            }
+          }
+          if (tail_part) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              wo_out[(cc * 8 + i) * 128] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(o[8 * i + 0], o[8 * i + 1]);
+              w.y = pack_bf16x2(o[8 * i + 2], o[8 * i + 3]);
+              w.z = pack_bf16x2(o[8 * i + 4], o[8 * i + 5]);
+              w.w = pack_bf16x2(o[8 * i + 6], o[8 * i + 7]);
+              *reinterpret_cast<uint4*>(orow + cc * 32 + i * 8) = w;
+            }
           }
         }
       }
+      if (flag_in != nullptr) st_release_u32(flag_in, 0u);  // consume: ready for the next launch
+      if (tail_part && row_ok) {
+        reinterpret_cast<float2*>(wsb_out + kWsOBytes)[ws_row] = make_float2(m_used, l);
+        __threadfence();
+        st_release_u32(reinterpret_cast<uint32_t*>(wsb_out + kWsOBytes + kWsMlBytes) + ws_row, 1u);
+      }
+      // O_t drained: the MMA warp may start the next segment's accumulation
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofree_bar(t));
     }
   }
 
@@ -412,7 +652,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 template <bool kPTmem>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const AttnParams& p, int n_heads, cudaStream_t stream) {
+                       const AttnParams& p, int grid, cudaStream_t stream) {
   using Cfg = AttnCfg<kPTmem>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -420,24 +660,51 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid((p.Lq + 255) / 256, n_heads);
-  attn_fwd_kernel<kPTmem><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
+  // partial-merge flag wait relies on
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  static const bool coop = getenv("LLB_ATTN_COOP") == nullptr || atoi(getenv("LLB_ATTN_COOP")) != 0;
+  cfg.numAttrs = coop ? 1 : 0;
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
 
 }  // namespace llb
 
+extern "C" int64_t llb_attn_workspace_bytes(void) {
+  const int sms = llb::device_sm_count();
+  return static_cast<int64_t>(sms > 0 ? sms : 148) * llb::kWsPerCta;
+}
+
 extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
-                            const llb_step_params* seg_dev, float scale, int variant,
-                            void* stream) {
+                            const llb_step_params* seg_dev, float scale, int variant, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(q && k && v && out && seg_dev, "attn: null tensor");
   LLB_CHECK_ARG(Lq > 0 && n_heads > 0 && kv_rows > 0, "attn: bad shape");
   LLB_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                 "attn: leading dims must be multiples of 8");
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attn: out must be 16-byte aligned");
+  const int sms = device_sm_count();
+  LLB_CHECK_ARG(sms > 0, "attn: no CUDA device");
+  const int n_pairs = (Lq + 255) / 256;
+  const int n_items = n_pairs * n_heads;
+  int grid = n_items < sms ? n_items : sms;
+  // debug knob (needs LLB_ATTN_COOP=0): one CTA per item instead of a persistent grid
+  if (getenv("LLB_ATTN_GRID_ITEMS") != nullptr && atoi(getenv("LLB_ATTN_GRID_ITEMS")) != 0) grid = n_items;
+  LLB_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(grid < sms ? grid : sms) * kWsPerCta &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                "attn: needs a 16-byte aligned workspace of llb_attn_workspace_bytes() bytes, zeroed once");
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_2d_bf16(&tq, q, Lq, static_cast<uint64_t>(n_heads) * 128, ldq, 128, 64);
   if (rc) return rc;
@@ -449,9 +716,12 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.Lq = Lq;
+  p.n_heads = n_heads;
+  p.n_pairs = n_pairs;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.segs = seg_dev;
+  p.workspace = static_cast<uint8_t*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (variant == 1) return launch_attn<false>(tq, tk, tv, p, n_heads, s);
-  return launch_attn<true>(tq, tk, tv, p, n_heads, s);
+  if (variant == 1) return launch_attn<false>(tq, tk, tv, p, grid, s);
+  return launch_attn<true>(tq, tk, tv, p, grid, s);
 }

@@ -137,24 +137,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+    // Whole warp in the loop (so descriptors stay in uniform registers); one elected lane issues.
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kStageA;
-          const uint64_t da = umma_desc_kmajor(sa);
-          const uint64_t db = umma_desc_kmajor(sb);
+        const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kStageA;
+        const uint64_t da = umma_desc_kmajor(sa);
+        const uint64_t db = umma_desc_kmajor(sb);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the
@@ -162,9 +163,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
             umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {

@@ -26,6 +26,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp.  Role loops keep the WHOLE warp in the loop and predicate
+// only the tcgen05 / TMA issue with this: descriptors and addresses computed by all lanes are then
+// provably warp-uniform and live in uniform registers, instead of the per-operand R2UR "waterfall"
+// loop ptxas emits for single-lane (`if (lane == 0)`) code.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));

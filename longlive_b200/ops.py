@@ -94,6 +94,22 @@ def step_params_tensor(sp: StepParams, device, out: Optional[torch.Tensor] = Non
     return out
 
 
+_ATTN_WS = {}
+
+
+def attention_workspace(device) -> torch.Tensor:
+    """Per-device scratch of llb_attn_fwd's stream-K split (zeroed once; flags are self-resetting).
+    One buffer per device is enough because launches on a stream are serialised."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        n = int(_lib.lib().llb_attn_workspace_bytes())
+        ws = torch.zeros(n, dtype=torch.uint8, device=dev)
+        _ATTN_WS[key] = ws
+    return ws
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch.Tensor, *,
               n_heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
               variant: int = 0) -> torch.Tensor:
@@ -106,10 +122,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch
         out = torch.empty((Lq, n_heads * 128), dtype=torch.bfloat16, device=q.device)
     if scale is None:
         scale = 128 ** -0.5
+    ws = attention_workspace(q.device)
     rc = _lib.lib().llb_attn_fwd(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
         out.data_ptr(), out.stride(0), Lq, n_heads, k.shape[0], segs_dev.data_ptr(),
-        C.c_float(scale), variant, _stream())
+        C.c_float(scale), variant, ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "llb_attn_fwd")
     return out
 

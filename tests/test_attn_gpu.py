@@ -51,6 +51,11 @@ ATTN_CASES = [
     (4680, 12, 512, [(0, 512)]),
     (1560, 3, 18720, [(0, 4680), (9360, 3120), (4680, 1000)]),
     (130, 1, 1000, [(5, 77), (300, 129)]),
+    # stream-K split paths: 228 / 888 items over 148 CTAs, ragged multi-range key sets
+    (4680, 12, 18720, [(0, 4680), (9360, 3120), (4680, 1000)]),
+    (18720, 12, 4680, [(0, 4680)]),
+    (4700, 12, 2100, [(0, 2100)]),
+    (38 * 256, 4, 4096, [(0, 4096)]),
 ]
 
 
@@ -70,6 +75,9 @@ def test_attention(Lq, H, rows, segs, variant):
     # P is rounded to bf16 before the PV product (as in flash-attn): ~3e-3 rel-L2 expected
     assert err < 8e-3, f"rel-L2 {err}"
     assert torch.isfinite(out.float()).all()
+    # the launch must leave the split workspace flags consumed (graph-replay safety): run again
+    out2 = ops.attention(q, k, v, sp, n_heads=H, variant=variant)
+    assert torch.equal(out, out2), "second launch on the same workspace differs"
 
 
 @pytest.mark.parametrize("variant", [0, 1], ids=["v0", "v1"])
