@@ -100,7 +100,7 @@ def run_reference(args):
 
     def one_forward(n_layers):
         cfg = wo.WanConfig(num_layers=n_layers)
-        m = wo.OracleModel(cfg, wo.init_state_dict(cfg, seed=0))
+        m = wo.OracleModel(cfg, wo.init_state_dict(cfg, seed=0), attention_impl="sdpa")
         kv = wo.new_kv_cache(cfg, 1, 12 * fs, "cpu")
         for c in kv:  # steady state: cache full, next chunk rolls
             c["global_end_index"].fill_(12 * fs); c["local_end_index"].fill_(12 * fs)
@@ -129,8 +129,8 @@ def run_reference(args):
     t_fwd = sum(times) / len(times) * (30.0 / n_layers)  # linear in layers (embeddings negligible)
     fps = 12.0 / (5.0 * t_fwd)  # one chunk = 5 forwards = 3 latent = 12 video frames
     sample = (f"{args.steps} timed forwards of {n_layers}/30 blocks (scaled x{30.0 / n_layers:.2f}) on one "
-              f"steady-state 3-latent-frame chunk (Lq 4680, Lk 18720, roll+evict); FPS = 12 video frames / "
-              f"(5 forwards x forward time)")
+              f"steady-state 3-latent-frame chunk (Lq 4680, Lk 18720, roll+evict), attention through torch SDPA "
+              f"as on the reference's CPU path; FPS = 12 video frames / (5 forwards x forward time)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_fwd * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -151,7 +151,7 @@ def cpu_baseline_sample():
     n_layers = 3
     cfg = wo.WanConfig(num_layers=n_layers)
     fs = cfg.frame_seqlen
-    m = wo.OracleModel(cfg, wo.init_state_dict(cfg, seed=0))
+    m = wo.OracleModel(cfg, wo.init_state_dict(cfg, seed=0), attention_impl="sdpa")
     kv = wo.new_kv_cache(cfg, 1, 12 * fs, "cpu")
     cc = wo.new_crossattn_cache(cfg, 1, "cpu")
     x = torch.randn(1, 16, 3, 60, 104).to(torch.bfloat16)
@@ -168,7 +168,7 @@ def cpu_baseline_sample():
     fps = 12.0 / (5.0 * t_fwd)
     return {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"2 timed forwards of {n_layers}/30 blocks (scaled x10) on a steady-state chunk "
-                      f"(Lq 4680, Lk 18720); FPS = 12 / (5 x forward time); {torch.get_num_threads()} threads"}
+                      f"(Lq 4680, Lk 18720), torch SDPA attention; FPS = 12 / (5 x forward time); {torch.get_num_threads()} threads"}
 
 
 def attention_roofline(torch, ops, dev, iters=60):
@@ -217,7 +217,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from longlive_b200 import ops, synth
+    from longlive_b200 import multistream, ops, synth
     from longlive_b200.model import CausalWanModel
     from longlive_b200.pipeline import CausalInferencePipeline
     from longlive_b200.wrapper import WanDiffusionWrapper
@@ -232,8 +232,9 @@ def run_ours(args):
     pargs = SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True,
                             num_frame_per_block=3, context_noise=0, global_sink=False,
                             model_kwargs=MK(local_attn_size=12, sink_size=3, timestep_shift=5.0))
-    embeds_host = synth.prompt_embeds(100 + rank).pin_memory()
-    noise_host = synth.latent_noise(rank, T_FRAMES).pin_memory()
+    noise_seed, prompt_seed = multistream.stream_seeds(multistream.stream_assignment(world, rank, world)[0])
+    embeds_host = synth.prompt_embeds(prompt_seed).pin_memory()
+    noise_host = synth.latent_noise(noise_seed, T_FRAMES).pin_memory()
     state = {}
 
     def text_encoder(text_prompts):
@@ -255,23 +256,15 @@ def run_ours(args):
         out_host.copy_(lat, non_blocking=True)
         return out_host
 
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, k):
-        sync_all()
+        multistream.barrier(dev)
         st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st.record()
         for _ in range(k):
             fn()
         en.record()
-        sync_all()
-        ms = torch.tensor([st.elapsed_time(en)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        multistream.barrier(dev)
+        return multistream.max_over_ranks(st.elapsed_time(en), dev)
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
