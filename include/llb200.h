@@ -99,6 +99,41 @@ typedef struct llb_step_params {
 } llb_step_params;
 
 /* ------------------------------------------------------------------------------------------
+ * Optional single-stream head parallelism (Ulysses-style; the reference's only
+ * sequence-parallel design is wan/distributed/xdit_context_parallel.py:131-192, for the non-causal
+ * model).  Tokens are sharded over ranks for every GEMM / row kernel, heads are sharded for
+ * attention and for the KV ring.  The two exchanges per block are FUSED into the producing kernels
+ * as direct stores into peer GPUs' (NVLink-mapped, symmetric) buffers:
+ *   llb_rmsnorm_rope_append  writes head h of Q / K / V to rank h / heads_per_rank,
+ *   llb_attn_fwd             writes output rows to the rank that owns those token rows,
+ * followed by llb_peer_barrier.  A null shard pointer means single-GPU operation.
+ * ------------------------------------------------------------------------------------------ */
+#define LLB_MAX_RANKS 8
+typedef struct llb_qkv_shard {
+  int32_t n_ranks;
+  int32_t heads_per_rank;
+  int32_t row0;                 /* global token row of local row 0                           */
+  int32_t reserved;
+  void* q_peers[LLB_MAX_RANKS]; /* rank r: Q buffer [L_total, heads_per_rank*128]              */
+  void* k_peers[LLB_MAX_RANKS]; /* rank r: K ring   [cache_rows, heads_per_rank*128]           */
+  void* v_peers[LLB_MAX_RANKS];
+} llb_qkv_shard;
+
+typedef struct llb_out_shard {
+  int32_t n_ranks;
+  int32_t rows_per_rank;          /* token rows owned by each rank                             */
+  int32_t head_col0;              /* first output column of this rank's heads (head0 * 128)    */
+  int32_t reserved;
+  int64_t ld_out;                 /* leading dimension of the peers' output buffers            */
+  void* out_peers[LLB_MAX_RANKS]; /* rank r: attention output [rows_per_rank, ld_out]          */
+} llb_out_shard;
+
+/* Device-side barrier across ranks: flags_peers (DEVICE array of n_ranks pointers) -> each rank's
+ * uint32[n_ranks] flag array in peer-mapped memory; epoch_local: this rank's uint32 counter.  Makes
+ * all earlier peer stores of every rank visible before any later kernel of any rank runs. */
+int llb_peer_barrier(void* const* flags_peers_dev, int rank, int n_ranks, void* epoch_local, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * GEMM family: out[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N]); bf16 in/out, fp32 accumulate
  * in TMEM (tcgen05.mma, TMA-fed).  Replaces nn.Linear at causal_model.py:90-93,122-126,364,
  * 406-408,492,601-608 and model.py:172-178,193 together with the elementwise ops that follow.
@@ -111,7 +146,7 @@ typedef struct llb_step_params {
 
 int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                   int M, int N, int K, int epilogue, const void* bias, const void* gate,
-                  int64_t ld_gate, int rows_per_gate, const void* res, int64_t ld_res,
+                  int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -126,7 +161,7 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
 int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                  int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
                  const llb_step_params* seg_dev, float scale, int variant, void* workspace,
-                 int64_t workspace_bytes, void* stream);
+                 int64_t workspace_bytes, const llb_out_shard* shard, void* stream);
 /* Size of the device workspace llb_attn_fwd needs (partial O / (m,l) / flags of the stream-K
  * split, one slice per SM).  Allocate once per device, zero it once, reuse for every launch on
  * streams that are ordered with respect to each other. */
@@ -137,10 +172,10 @@ int64_t llb_attn_workspace_bytes(void);
  * ------------------------------------------------------------------------------------------ */
 /* LayerNorm(eps, no affine) then x*(1+scale)+shift per frame  (causal_model.py:445, 463-464, 507)
  * or, with ln_w/ln_b non-null and shift/scale null, affine LayerNorm (norm3, :460).
- * shift/scale: [n_frames, ld_mod] rows selected by row / rows_per_frame. */
+ * shift/scale: [n_frames, ld_mod] rows selected by (row0 + row) / rows_per_frame. */
 int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
                     const void* shift, const void* scale, int64_t ld_mod, int rows_per_frame,
-                    const void* ln_w, const void* ln_b, float eps, void* stream);
+                    int row0, const void* ln_w, const void* ln_b, float eps, void* stream);
 
 /* Fused WanRMSNorm(q), WanRMSNorm(k) (model.py:78-86), causal_rope_apply (causal_model.py:32-60)
  * and the KV-cache insert (:268-269 / :310-311) in one pass over the fused QKV GEMM output.
@@ -151,7 +186,8 @@ int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows
 int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_out, int64_t ldq,
                             void* k_cache, void* v_cache, int64_t ld_cache, int rows, int n_heads,
                             const void* wq, const void* wk, float eps, const void* rope_cs,
-                            int grid_h, int grid_w, const llb_step_params* p_dev, void* stream);
+                            int grid_h, int grid_w, const llb_step_params* p_dev,
+                            const llb_qkv_shard* shard, void* stream);
 
 /* Plain WanRMSNorm over C channels: out = bf16(x * rsqrt(mean(x^2)+eps)) * w  (model.py:78-86). */
 int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,

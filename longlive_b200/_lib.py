@@ -76,6 +76,22 @@ class StepParams(C.Structure):
 
 
 STEP_PARAMS_INT32 = C.sizeof(StepParams) // 4
+LLB_MAX_RANKS = 8
+
+
+class QkvShard(C.Structure):
+    """llb_qkv_shard: head-parallel destination table of llb_rmsnorm_rope_append."""
+
+    _fields_ = [("n_ranks", C.c_int32), ("heads_per_rank", C.c_int32), ("row0", C.c_int32),
+                ("reserved", C.c_int32), ("q_peers", C.c_void_p * LLB_MAX_RANKS),
+                ("k_peers", C.c_void_p * LLB_MAX_RANKS), ("v_peers", C.c_void_p * LLB_MAX_RANKS)]
+
+
+class OutShard(C.Structure):
+    """llb_out_shard: head-parallel destination table of llb_attn_fwd."""
+
+    _fields_ = [("n_ranks", C.c_int32), ("rows_per_rank", C.c_int32), ("head_col0", C.c_int32),
+                ("reserved", C.c_int32), ("ld_out", C.c_int64), ("out_peers", C.c_void_p * LLB_MAX_RANKS)]
 
 _PROTOS = {
     # name: (restype, argtypes)
@@ -91,25 +107,27 @@ _PROTOS = {
     "llb_gemm_bf16": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
-         C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
+         C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
     ),
     "llb_attn_fwd": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
-         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
+         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int64,
+         C.POINTER(OutShard), C.c_void_p],
     ),
     "llb_attn_workspace_bytes": (C.c_int64, []),
     "llb_ln_modulate": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-         C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
+         C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p],
     ),
     "llb_rmsnorm_rope_append": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
          C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-         C.c_void_p],
+         C.POINTER(QkvShard), C.c_void_p],
     ),
+    "llb_peer_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "llb_rmsnorm": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p],

@@ -39,6 +39,7 @@
 #include "llb_host.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace llb {
 
@@ -69,6 +70,7 @@ struct AttnParams {
   float scale_log2;
   const llb_step_params* segs;
   uint8_t* workspace;  // gridDim.x * kWsPerCta bytes, flags zero-initialised once
+  llb_out_shard shard; // n_ranks == 1: single GPU
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -593,6 +595,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         a_oth *= inv;
       }
       __nv_bfloat16* orow = p.out + static_cast<int64_t>(grow) * p.ldo + head * 128;
+      if (p.shard.n_ranks > 1 && row_ok) {
+        // head-parallel mode: the return exchange is fused into the store - this token row belongs
+        // to rank grow / rows_per_rank; write our heads' columns into its (peer-mapped) buffer
+        const int r = grow / p.shard.rows_per_rank;
+        orow = static_cast<__nv_bfloat16*>(p.shard.out_peers[r]) +
+               static_cast<int64_t>(grow - r * p.shard.rows_per_rank) * p.shard.ld_out + p.shard.head_col0 +
+               head * 128;
+      }
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t ov[32];
@@ -688,7 +698,7 @@ extern "C" int64_t llb_attn_workspace_bytes(void) {
 extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
                             const llb_step_params* seg_dev, float scale, int variant, void* workspace,
-                            int64_t workspace_bytes, void* stream) {
+                            int64_t workspace_bytes, const llb_out_shard* shard, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(q && k && v && out && seg_dev, "attn: null tensor");
   LLB_CHECK_ARG(Lq > 0 && n_heads > 0 && kv_rows > 0, "attn: bad shape");
@@ -699,10 +709,12 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   LLB_CHECK_ARG(sms > 0, "attn: no CUDA device");
   const int n_pairs = (Lq + 255) / 256;
   const int n_items = n_pairs * n_heads;
-  int grid = n_items < sms ? n_items : sms;
+  // one CTA per SM; when there are fewer items than SMs the scheduler splits every item's kv range
+  // (rounds = 0, all items are "remainder"), CTAs without work exit immediately
+  int grid = sms;
   // debug knob (needs LLB_ATTN_COOP=0): one CTA per item instead of a persistent grid
   if (getenv("LLB_ATTN_GRID_ITEMS") != nullptr && atoi(getenv("LLB_ATTN_GRID_ITEMS")) != 0) grid = n_items;
-  LLB_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(grid < sms ? grid : sms) * kWsPerCta &&
+  LLB_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(sms) * kWsPerCta &&
                     (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                 "attn: needs a 16-byte aligned workspace of llb_attn_workspace_bytes() bytes, zeroed once");
   CUtensorMap tq, tk, tv;
@@ -721,6 +733,15 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.scale_log2 = scale * 1.4426950408889634f;
   p.segs = seg_dev;
   p.workspace = static_cast<uint8_t*>(workspace);
+  memset(&p.shard, 0, sizeof(p.shard));
+  p.shard.n_ranks = 1;
+  if (shard != nullptr && shard->n_ranks > 1) {
+    LLB_CHECK_ARG(shard->n_ranks <= LLB_MAX_RANKS && shard->rows_per_rank > 0 && shard->ld_out % 8 == 0 &&
+                      shard->head_col0 % 8 == 0, "attn: bad output shard description");
+    for (int r = 0; r < shard->n_ranks; ++r)
+      LLB_CHECK_ARG(shard->out_peers[r] != nullptr, "attn: null peer pointer");
+    p.shard = *shard;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (variant == 1) return launch_attn<false>(tq, tk, tv, p, grid, s);
   return launch_attn<true>(tq, tk, tv, p, grid, s);

@@ -50,6 +50,7 @@ struct GemmParams {
   const __nv_bfloat16* gate;
   int64_t ld_gate;
   int rows_per_gate;
+  int gate_row0;
   const __nv_bfloat16* res;
   int64_t ld_res;
   int num_m_tiles, num_n_tiles;
@@ -239,7 +240,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
               uint4 gt = make_uint4(0, 0, 0, 0);
               if (epi == LLB_EPI_BIAS_GATE_RES) {
                 gt = __ldg(reinterpret_cast<const uint4*>(
-                    p.gate + static_cast<int64_t>(grow / p.rows_per_gate) * p.ld_gate + gcol));
+                    p.gate + static_cast<int64_t>((grow + p.gate_row0) / p.rows_per_gate) * p.ld_gate + gcol));
               }
               const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
               const uint32_t* xx = reinterpret_cast<const uint32_t*>(&x);
@@ -295,8 +296,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
                              int64_t ldo, int M, int N, int K, int epilogue, const void* bias,
-                             const void* gate, int64_t ld_gate, int rows_per_gate, const void* res,
-                             int64_t ld_res, void* stream) {
+                             const void* gate, int64_t ld_gate, int rows_per_gate, int gate_row0,
+                             const void* res, int64_t ld_res, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(A && W && out, "gemm: null tensor");
   LLB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -336,6 +337,7 @@ extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.gate = static_cast<const __nv_bfloat16*>(gate); p.ld_gate = ld_gate;
   p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  p.gate_row0 = gate_row0;
   p.res = static_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;

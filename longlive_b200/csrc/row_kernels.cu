@@ -6,6 +6,8 @@
 #include "llb_common.cuh"
 #include "llb_host.h"
 
+#include <string.h>
+
 namespace llb {
 
 constexpr int kRowWarps = 8;  // rows per CTA
@@ -26,8 +28,8 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                    int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ shift,
                    const __nv_bfloat16* __restrict__ scale, int64_t ld_mod, int rows_per_frame,
-                   const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
-                   float eps) {
+                   int row0, const __nv_bfloat16* __restrict__ ln_w,
+                   const __nv_bfloat16* __restrict__ ln_b, float eps) {
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -61,7 +63,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
   }
   const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
   const bool affine = ln_w != nullptr;
-  const int64_t mrow = static_cast<int64_t>(row / rows_per_frame) * ld_mod;
+  const int64_t mrow = static_cast<int64_t>((row0 + row) / rows_per_frame) * ld_mod;
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
@@ -179,7 +181,7 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
                            int64_t ld_cache, int rows, int C,
                            const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
                            float eps, const float2* __restrict__ rope_cs, int grid_h, int grid_w,
-                           const llb_step_params* __restrict__ sp) {
+                           const llb_step_params* __restrict__ sp, const llb_qkv_shard sh) {
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -199,16 +201,19 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
   const float q_rstd = rsqrtf(row_sumsq(qv, lane, nvec) / static_cast<float>(C) + eps);
   const float k_rstd = rsqrtf(row_sumsq(kv, lane, nvec) / static_cast<float>(C) + eps);
 
-  // token -> (frame, h, w), row-major over (frames, grid_h, grid_w)
+  // token -> (frame, h, w), row-major over (frames, grid_h, grid_w); grow = row in the whole chunk
+  const int grow = sh.row0 + row;
   const int hw = grid_h * grid_w;
-  const int f = row / hw, rem = row - f * hw;
+  const int f = grow / hw, rem = grow - f * hw;
   const int ph = rem / grid_w, pw = rem - ph * grid_w;
   const int pf = sp->rope_start_frame + f;
-  const int dst = k_cache != nullptr ? ring_dst_row(sp, row) : -1;
+  const bool sharded = sh.n_ranks > 1;
+  const int dst = (k_cache != nullptr || sharded) ? ring_dst_row(sp, grow) : -1;
+  const int vec_per_rank = sh.heads_per_rank * 16;  // 16-byte vectors per rank's head slice
 
   uint4* qo = reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq);
-  uint4* ko = dst >= 0 ? reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
-  uint4* vo = dst >= 0 ? reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
+  uint4* ko = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
+  uint4* vo = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int vi = lane + i * 32;
@@ -235,10 +240,24 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
         oq[e] = pack_bf16x2(qa * cs.x - qb * cs.y, qa * cs.y + qb * cs.x);
         ok[e] = pack_bf16x2(ka * cs.x - kb * cs.y, ka * cs.y + kb * cs.x);
       }
-      qo[vi] = make_uint4(oq[0], oq[1], oq[2], oq[3]);
-      if (dst >= 0) {
-        ko[vi] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
-        vo[vi] = vr[vi];
+      if (!sharded) {
+        qo[vi] = make_uint4(oq[0], oq[1], oq[2], oq[3]);
+        if (dst >= 0) {
+          ko[vi] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
+          vo[vi] = vr[vi];
+        }
+      } else {
+        // head exchange fused into the store: this 16-byte vector belongs to head vi/16, owned by
+        // rank (vi/16)/heads_per_rank; write it straight into that rank's (peer-mapped) buffers
+        const int r = vi / vec_per_rank, lv = vi - r * vec_per_rank;
+        const int64_t ldp = static_cast<int64_t>(vec_per_rank);  // peer leading dim in uint4 units
+        reinterpret_cast<uint4*>(sh.q_peers[r])[static_cast<int64_t>(grow) * ldp + lv] =
+            make_uint4(oq[0], oq[1], oq[2], oq[3]);
+        if (dst >= 0) {
+          reinterpret_cast<uint4*>(sh.k_peers[r])[static_cast<int64_t>(dst) * ldp + lv] =
+              make_uint4(ok[0], ok[1], ok[2], ok[3]);
+          reinterpret_cast<uint4*>(sh.v_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = vr[vi];
+        }
       }
     }
   }
@@ -314,14 +333,51 @@ __global__ void silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
   out[idx] = __float2bfloat16_rn(v / (1.0f + expf(-v)));
 }
 
+// Cross-rank barrier over peer-mapped flags (one CTA, thread j talks to rank j).
+__global__ void peer_barrier_kernel(uint32_t* const* __restrict__ flags_peers, int rank, int n_ranks,
+                                    uint32_t* __restrict__ epoch_local) {
+  __shared__ uint32_t e_sh;
+  if (threadIdx.x == 0) e_sh = *epoch_local + 1;
+  __syncthreads();
+  const uint32_t e = e_sh;
+  const int j = threadIdx.x;
+  if (j < n_ranks) {
+    __threadfence_system();  // order this rank's earlier peer stores before the signal
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags_peers[j] + rank), "r"(e) : "memory");
+    const uint32_t* mine = flags_peers[rank] + j;
+    uint32_t v, spins = 0;
+    uint64_t t0 = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((++spins & 0xfffu) == 0) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 5 * LLB_WAIT_TIMEOUT_NS) __trap();
+      }
+    } while (static_cast<int32_t>(v - e) < 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch_local = e;
+}
+
 }  // namespace llb
 
 using namespace llb;
 
+extern "C" int llb_peer_barrier(void* const* flags_peers_dev, int rank, int n_ranks, void* epoch_local,
+                                void* stream) {
+  LLB_CHECK_ARG(flags_peers_dev && epoch_local && n_ranks >= 1 && n_ranks <= LLB_MAX_RANKS && rank >= 0 &&
+                    rank < n_ranks, "peer_barrier: bad arguments");
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uint32_t* const*>(flags_peers_dev), rank, n_ranks, static_cast<uint32_t*>(epoch_local));
+  LLB_LAUNCH_CHECK("peer_barrier_kernel");
+  return LLB_OK;
+}
+
 extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
                                const void* shift, const void* scale, int64_t ld_mod,
-                               int rows_per_frame, const void* ln_w, const void* ln_b, float eps,
-                               void* stream) {
+                               int rows_per_frame, int row0, const void* ln_w, const void* ln_b,
+                               float eps, void* stream) {
   LLB_CHECK_ARG(x && out && rows > 0, "ln_modulate: null tensor / no rows");
   LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "ln_modulate: C=%d unsupported", C);
   LLB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ld_mod % 8 == 0, "ln_modulate: leading dims % 8");
@@ -332,7 +388,7 @@ extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ld
   ln_modulate_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
-      rows_per_frame > 0 ? rows_per_frame : 1, static_cast<const __nv_bfloat16*>(ln_w),
+      rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
       static_cast<const __nv_bfloat16*>(ln_b), eps);
   LLB_LAUNCH_CHECK("ln_modulate_kernel");
   return LLB_OK;
@@ -355,9 +411,21 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
                                        void* k_cache, void* v_cache, int64_t ld_cache, int rows,
                                        int n_heads, const void* wq, const void* wk, float eps,
                                        const void* rope_cs, int grid_h, int grid_w,
-                                       const llb_step_params* p_dev, void* stream) {
-  LLB_CHECK_ARG(qkv && q_out && wq && wk && rope_cs && p_dev && rows > 0,
+                                       const llb_step_params* p_dev, const llb_qkv_shard* shard,
+                                       void* stream) {
+  LLB_CHECK_ARG(qkv && wq && wk && rope_cs && p_dev && rows > 0 && (q_out || shard),
                 "rmsnorm_rope_append: null tensor / no rows");
+  llb_qkv_shard sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.n_ranks = 1;
+  sh.heads_per_rank = n_heads;
+  if (shard != nullptr) {
+    sh = *shard;
+    LLB_CHECK_ARG(sh.n_ranks >= 1 && sh.n_ranks <= LLB_MAX_RANKS && sh.heads_per_rank * sh.n_ranks == n_heads,
+                  "rmsnorm_rope_append: bad shard description");
+    for (int r = 0; r < sh.n_ranks && sh.n_ranks > 1; ++r)
+      LLB_CHECK_ARG(sh.q_peers[r] && sh.k_peers[r] && sh.v_peers[r], "rmsnorm_rope_append: null peer pointer");
+  }
   const int C = n_heads * 128;
   LLB_CHECK_ARG(C <= 32 * kMaxVec * 8, "rmsnorm_rope_append: n_heads=%d unsupported", n_heads);
   LLB_CHECK_ARG((k_cache == nullptr) == (v_cache == nullptr), "rmsnorm_rope_append: k/v cache mismatch");
@@ -368,7 +436,7 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
       static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(q_out), ldq,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), ld_cache, rows, C,
       static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), eps,
-      static_cast<const float2*>(rope_cs), grid_h, grid_w, p_dev);
+      static_cast<const float2*>(rope_cs), grid_h, grid_w, p_dev, sh);
   LLB_LAUNCH_CHECK("rmsnorm_rope_append_kernel");
   return LLB_OK;
 }

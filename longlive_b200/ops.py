@@ -47,7 +47,7 @@ def launch_count() -> int:
 # ------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
-         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0,
+         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0, gate_row0: int = 0,
          res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  a/w/out 2-D bf16 (row stride arbitrary)."""
     _req(a, "a"); _req(w, "w")
@@ -63,7 +63,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     rc = _lib.lib().llb_gemm_bf16(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
         M, N, K, epilogue, _ptr(bias), _ptr(gate), gate.stride(0) if gate is not None else 0,
-        rows_per_gate, _ptr(res), res.stride(0) if res is not None else 0, _stream())
+        rows_per_gate, gate_row0, _ptr(res), res.stride(0) if res is not None else 0, _stream())
     _lib.check(rc, "llb_gemm_bf16")
     return out
 
@@ -112,8 +112,9 @@ def attention_workspace(device) -> torch.Tensor:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch.Tensor, *,
               n_heads: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None,
-              variant: int = 0) -> torch.Tensor:
-    """q [Lq, H*128], k/v [rows, H*128] (any row stride), segs_dev: int32 StepParams tensor."""
+              variant: int = 0, shard=None) -> torch.Tensor:
+    """q [Lq, H*128], k/v [rows, H*128] (any row stride), segs_dev: int32 StepParams tensor.
+    shard (head-parallel mode): _lib.OutShard; output rows then go to the peers' buffers."""
     _req(q, "q"); _req(k, "k"); _req(v, "v")
     assert segs_dev.dtype == torch.int32 and segs_dev.numel() >= STEP_PARAMS_INT32 and segs_dev.is_cuda
     Lq = q.shape[0]
@@ -126,14 +127,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch
     rc = _lib.lib().llb_attn_fwd(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
         out.data_ptr(), out.stride(0), Lq, n_heads, k.shape[0], segs_dev.data_ptr(),
-        C.c_float(scale), variant, ws.data_ptr(), ws.numel(), _stream())
+        C.c_float(scale), variant, ws.data_ptr(), ws.numel(),
+        C.byref(shard) if shard is not None else None, _stream())
     _lib.check(rc, "llb_attn_fwd")
     return out
 
 
 # ------------------------------------------------------------------------------------------------
 def ln_modulate(x: torch.Tensor, *, shift: Optional[torch.Tensor] = None,
-                scale: Optional[torch.Tensor] = None, rows_per_frame: int = 0,
+                scale: Optional[torch.Tensor] = None, rows_per_frame: int = 0, row0: int = 0,
                 ln_w: Optional[torch.Tensor] = None, ln_b: Optional[torch.Tensor] = None,
                 eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(x, "x")
@@ -147,7 +149,7 @@ def ln_modulate(x: torch.Tensor, *, shift: Optional[torch.Tensor] = None,
         ld_mod = shift.stride(0)
     rc = _lib.lib().llb_ln_modulate(
         x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, Cc, _ptr(shift), _ptr(scale),
-        ld_mod, rows_per_frame, _ptr(ln_w), _ptr(ln_b), C.c_float(eps), _stream())
+        ld_mod, rows_per_frame, row0, _ptr(ln_w), _ptr(ln_b), C.c_float(eps), _stream())
     _lib.check(rc, "llb_ln_modulate")
     return out
 
@@ -164,12 +166,15 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6,
     return out
 
 
-def rmsnorm_rope_append(qkv: torch.Tensor, q_out: torch.Tensor, k_cache: Optional[torch.Tensor],
+def rmsnorm_rope_append(qkv: torch.Tensor, q_out: Optional[torch.Tensor], k_cache: Optional[torch.Tensor],
                         v_cache: Optional[torch.Tensor], wq: torch.Tensor, wk: torch.Tensor,
                         rope_cs: torch.Tensor, grid_hw: Tuple[int, int], params_dev: torch.Tensor, *,
-                        n_heads: int, eps: float = 1e-6) -> torch.Tensor:
-    """qkv [rows, 3*H*128]; q_out [rows, H*128]; k_cache/v_cache [cache_rows, H*128]."""
-    _req(qkv, "qkv"); _req(q_out, "q_out")
+                        n_heads: int, eps: float = 1e-6, shard=None) -> Optional[torch.Tensor]:
+    """qkv [rows, 3*H*128]; q_out [rows, H*128]; k_cache/v_cache [cache_rows, H*128].
+    shard (head-parallel mode): _lib.QkvShard with the peers' Q / K / V base pointers."""
+    _req(qkv, "qkv")
+    if q_out is not None:
+        _req(q_out, "q_out")
     assert rope_cs.dtype == torch.float32 and rope_cs.is_cuda and rope_cs.is_contiguous()
     rows = qkv.shape[0]
     ld_cache = 0
@@ -178,9 +183,10 @@ def rmsnorm_rope_append(qkv: torch.Tensor, q_out: torch.Tensor, k_cache: Optiona
         assert k_cache.stride(0) == v_cache.stride(0)
         ld_cache = k_cache.stride(0)
     rc = _lib.lib().llb_rmsnorm_rope_append(
-        qkv.data_ptr(), qkv.stride(0), q_out.data_ptr(), q_out.stride(0), _ptr(k_cache), _ptr(v_cache),
-        ld_cache, rows, n_heads, wq.data_ptr(), wk.data_ptr(), C.c_float(eps), rope_cs.data_ptr(),
-        grid_hw[0], grid_hw[1], params_dev.data_ptr(), _stream())
+        qkv.data_ptr(), qkv.stride(0), _ptr(q_out), q_out.stride(0) if q_out is not None else 0,
+        _ptr(k_cache), _ptr(v_cache), ld_cache, rows, n_heads, wq.data_ptr(), wk.data_ptr(), C.c_float(eps),
+        rope_cs.data_ptr(), grid_hw[0], grid_hw[1], params_dev.data_ptr(),
+        C.byref(shard) if shard is not None else None, _stream())
     _lib.check(rc, "llb_rmsnorm_rope_append")
     return q_out
 
@@ -242,6 +248,12 @@ def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     rc = _lib.lib().llb_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
     _lib.check(rc, "llb_silu")
     return out
+
+
+def peer_barrier(flags_peers_dev: torch.Tensor, rank: int, n_ranks: int, epoch: torch.Tensor) -> None:
+    """flags_peers_dev: int64 device tensor with every rank's flag-array address; epoch: uint32[1]."""
+    rc = _lib.lib().llb_peer_barrier(flags_peers_dev.data_ptr(), rank, n_ranks, epoch.data_ptr(), _stream())
+    _lib.check(rc, "llb_peer_barrier")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -140,8 +140,8 @@ class CausalInferencePipeline(torch.nn.Module):
         heads, hd = getattr(model, "num_heads", 12), 128
         n = self.num_transformer_blocks
         old = self.kv_cache1
-        if (old is not None and len(old) == n and old[0]["k"].shape == (batch_size, size, heads, hd)
-                and old[0]["k"].dtype == dtype and old[0]["k"].device == torch.device(device)
+        if (old is not None and not hasattr(model, "allocate_kv_cache") and len(old) == n
+                and old[0]["k"].shape == (batch_size, size, heads, hd) and old[0]["k"].dtype == dtype and old[0]["k"].device == torch.device(device)
                 and "_llb_index_tensor" in old[0]):
             # same geometry as the previous video: re-zero in place (keeps device pointers, so the
             # model's captured CUDA graphs stay valid) instead of re-allocating 3.5 GB
@@ -149,6 +149,9 @@ class CausalInferencePipeline(torch.nn.Module):
                 c["k"].zero_(); c["v"].zero_()
             old[0]["_llb_index_tensor"].zero_()
             old[0].pop("_llb_ring", None); old[0].pop("_llb_published", None)
+            return
+        if hasattr(model, "allocate_kv_cache"):  # head-parallel model: head-sharded symmetric ring
+            self.kv_cache1 = model.allocate_kv_cache(batch_size, size, dtype, device)
             return
         index = torch.zeros(n, 2, dtype=torch.long, device=device)
         cache = []

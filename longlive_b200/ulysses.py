@@ -1,0 +1,177 @@
+"""Optional single-stream head parallelism over P GPUs of one NVLink/NVSwitch box.
+
+Model after the reference's only sequence-parallel code, the Ulysses scheme of
+wan/distributed/xdit_context_parallel.py:131-192 (never wired to the causal model there): tokens
+are sharded L/P per rank for every GEMM and row kernel (weights replicated), heads are sharded
+12/P per rank for self-attention and for the KV ring (cache memory / P).
+
+B200-native twist: there is no all-to-all on the data path.  The two exchanges per block are fused
+into the producing kernels as direct stores into the peers' symmetric (NVLink-mapped) buffers:
+  llb_rmsnorm_rope_append  sends head h of the roped Q and of K / V to rank h // (12/P): Q into
+                           that rank's [L, 12/P*128] query buffer, K / V straight into its ring rows;
+  llb_attn_fwd             returns output rows to the rank that owns the token rows,
+each followed by llb_peer_barrier (a one-CTA flag exchange over the same mapping).  NCCL
+(torch.distributed) is only used to set up the symmetric allocation and to all-gather the final
+[L, 64] head output.  Cross-attention needs no exchange (text K/V are replicated).
+
+Every rank runs the same pipeline code on the same inputs (same seeds), so host-side ring plans
+are identical; P must divide the head count and the tokens per chunk (P in {2, 4} for Wan-1.3B).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .model import CausalWanModel
+
+
+class SymmetricArena:
+    """One symmetric allocation per rank, bump-allocated; gives local tensor views and peer addresses."""
+
+    def __init__(self, nbytes: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert self.ptrs[self.rank] == self.buf.data_ptr()
+        self.off = 0
+        self.nbytes = nbytes
+
+    def alloc(self, shape, dtype) -> "SymTensor":
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        off = (self.off + 255) // 256 * 256
+        assert off + nbytes <= self.nbytes, "symmetric arena too small"
+        self.off = off + nbytes
+        local = self.buf[off:off + nbytes].view(dtype).view(*shape)
+        return SymTensor(local, [p + off for p in self.ptrs])
+
+
+class SymTensor:
+    def __init__(self, local: torch.Tensor, peer_ptrs: List[int]):
+        self.local, self.peer_ptrs = local, peer_ptrs
+
+
+class UlyssesCausalWanModel(CausalWanModel):
+    """CausalWanModel whose forward is split over the ranks of `group` (see module docstring)."""
+
+    def setup_parallel(self, group=None, max_tokens: int = 12 * 1560, cache_tokens: int = 12 * 1560,
+                       use_cuda_graph: bool = False):
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.P = dist.get_rank(self.group), dist.get_world_size(self.group)
+        assert self.num_heads % self.P == 0 and self.P <= _lib.LLB_MAX_RANKS
+        self.hp = self.num_heads // self.P
+        dev = self.patch_embedding.weight.device
+        hw = self.hp * 128
+        kv_bytes = self.num_layers * 2 * cache_tokens * hw * 2
+        need = kv_bytes + max_tokens * hw * 2 + (max_tokens // self.P + 8) * self.dim * 2 + (1 << 20)
+        self.arena = SymmetricArena(need, dev, self.group)
+        self.q_sym = self.arena.alloc((max_tokens, hw), torch.bfloat16)
+        self.attn_sym = self.arena.alloc((max_tokens // self.P + 8, self.dim), torch.bfloat16)
+        self.k_sym = [self.arena.alloc((cache_tokens, hw), torch.bfloat16) for _ in range(self.num_layers)]
+        self.v_sym = [self.arena.alloc((cache_tokens, hw), torch.bfloat16) for _ in range(self.num_layers)]
+        self.flags = self.arena.alloc((_lib.LLB_MAX_RANKS,), torch.int32)
+        self.flag_ptrs_dev = torch.tensor(self.flags.peer_ptrs, dtype=torch.int64, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cache_tokens = cache_tokens
+        # graph capture also records the NCCL all-gather of the head output and the peer barriers
+        self.use_cuda_graph = use_cuda_graph
+        dist.barrier(self.group)
+        torch.cuda.synchronize()
+        return self
+
+    # ---- cache allocation hook used by the pipelines: head-sharded ring in symmetric memory
+    def allocate_kv_cache(self, batch_size: int, size: int, dtype, device):
+        assert batch_size == 1 and size <= self.cache_tokens and dtype == torch.bfloat16
+        index = torch.zeros(self.num_layers, 2, dtype=torch.long, device=device)
+        cache = []
+        for i in range(self.num_layers):
+            k = self.k_sym[i].local[:size].view(1, size, self.hp, 128)
+            v = self.v_sym[i].local[:size].view(1, size, self.hp, 128)
+            k.zero_(); v.zero_()
+            cache.append({"k": k, "v": v, "global_end_index": index[i, 0:1], "local_end_index": index[i, 1:2]})
+        cache[0]["_llb_index_tensor"] = index
+        return cache
+
+    def _barrier(self):
+        ops.peer_barrier(self.flag_ptrs_dev, self.rank, self.P, self.epoch)
+
+    def _run_blocks(self, b: dict, kv_cache, crossattn_cache, B: int, F: int, H: int, W: int):
+        assert B == 1, "head-parallel mode handles one stream"
+        Pk = self._packed
+        C_, eps = self.dim, self.eps
+        gh, gw = H // 2, W // 2
+        fs = gh * gw
+        L = F * fs
+        P, r = self.P, self.rank
+        assert L % P == 0, "tokens per chunk must divide evenly over the ranks"
+        Lp = L // P
+        r0 = r * Lp
+        rows = slice(0, Lp)
+        hw = self.hp * 128
+        v = self.attn_variant
+        # embeddings: every rank patchifies the (replicated) input, then works on its own rows
+        ops.patchify(b["x_in"][0], out=b["patches"][:L])
+        x, xm = b["x"][rows], b["xm"][rows]
+        ops.gemm(b["patches"][r0:r0 + Lp], Pk["patch_w"], Pk["patch_b"], out=x)
+        ops.sinusoidal(b["t_in"], self.freq_dim, out=b["temb"])
+        ops.gemm(b["temb"], Pk["time0_w"], Pk["time0_b"], epilogue=ops.EPI_BIAS_SILU, out=b["te1"])
+        ops.gemm(b["te1"], Pk["time1_w"], Pk["time1_b"], out=b["e"])
+        ops.silu(b["e"], out=b["es"])
+        ops.gemm(b["es"], Pk["tproj_w"], Pk["tproj_b"], out=b["e0"])
+        ops.modulation_table(Pk["mod_all"], b["e0"], out=b["mod"])
+        qkv, qbuf, cq, h = b["qkv"][rows], b["q"][rows], b["cq"][rows], b["h"][rows]
+        attn_local = self.attn_sym.local[:Lp]
+        q_full = self.q_sym.local[:L]
+        out_sh = _lib.OutShard()
+        out_sh.n_ranks, out_sh.rows_per_rank, out_sh.head_col0, out_sh.ld_out = P, Lp, r * hw, C_
+        for j in range(P):
+            out_sh.out_peers[j] = self.attn_sym.peer_ptrs[j]
+        for i, lw in enumerate(Pk["layers"]):
+            m = b["mod"][i]
+            e = [m[:, k * C_:(k + 1) * C_] for k in range(6)]
+            ops.ln_modulate(x, shift=e[0], scale=e[1], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
+            ops.gemm(xm, lw["qkv_w"], lw["qkv_b"], out=qkv)
+            sh = _lib.QkvShard()
+            sh.n_ranks, sh.heads_per_rank, sh.row0 = P, self.hp, r0
+            for j in range(P):
+                sh.q_peers[j] = self.q_sym.peer_ptrs[j]
+                sh.k_peers[j] = self.k_sym[i].peer_ptrs[j]
+                sh.v_peers[j] = self.v_sym[i].peer_ptrs[j]
+            ops.rmsnorm_rope_append(qkv, None, None, None, lw["nq"], lw["nk"], Pk["rope"], (gh, gw), b["params"],
+                                    n_heads=self.num_heads, eps=eps, shard=sh)
+            self._barrier()  # every rank's head slices (Q, K, V) have landed
+            k2 = kv_cache[i]["k"][0].view(-1, hw)
+            v2 = kv_cache[i]["v"][0].view(-1, hw)
+            ops.attention(q_full, k2, v2, b["params"], n_heads=self.hp, out=q_full, variant=v, shard=out_sh)
+            self._barrier()  # every rank's token rows of the attention output have landed
+            ops.gemm(attn_local, lw["o_w"], lw["o_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2],
+                     rows_per_gate=fs, gate_row0=r0, res=x, out=x)
+            ops.ln_modulate(x, ln_w=lw["n3_w"], ln_b=lw["n3_b"], eps=eps, out=xm)
+            ops.gemm(xm, lw["cq_w"], lw["cq_b"], out=cq)
+            ops.rmsnorm(cq, lw["cnq"], eps, out=qbuf)
+            ck, cv = crossattn_cache[i]["k"], crossattn_cache[i]["v"]
+            ops.attention(qbuf, ck[0].view(-1, C_), cv[0].view(-1, C_), Pk["cross_segs"], n_heads=self.num_heads,
+                          out=b["attn"][rows], variant=v)
+            ops.gemm(b["attn"][rows], lw["co_w"], lw["co_b"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+            ops.ln_modulate(x, shift=e[3], scale=e[4], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
+            ops.gemm(xm, lw["f1_w"], lw["f1_b"], epilogue=ops.EPI_BIAS_GELU, out=h)
+            ops.gemm(h, lw["f2_w"], lw["f2_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
+                     gate_row0=r0, res=x, out=x)
+        b["e2"][:, :C_].copy_(b["e"]); b["e2"][:, C_:].copy_(b["e"])
+        ops.modulation_table(Pk["head_mod"], b["e2"], out=b["hmod"])
+        hm = b["hmod"][0]
+        ops.ln_modulate(x, shift=hm[:, :C_], scale=hm[:, C_:], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
+        ops.gemm(xm, Pk["head_w"], Pk["head_b"], out=b["y"][r0:r0 + Lp])
+        # gather the [L, 64] head output (tiny) so every rank can unpatchify the full chunk
+        dist.all_gather_into_tensor(b["y"][:L], b["y"][r0:r0 + Lp].clone(), group=self.group)
+        ops.unpatchify(b["y"][:L], self.out_dim, F, H, W, out=b["out"][0])
