@@ -75,8 +75,14 @@ def main():
         os.makedirs("gpurun_out", exist_ok=True)
         json.dump(res, open(f"gpurun_out/ulysses_P{world}_graph{a.graph}.json", "w"), indent=1)
         print(json.dumps(res))
-    assert max(errs) < 1e-2, errs
-    dist.destroy_process_group()
+    ok = max(errs) < 1e-2
+    # captured graphs hold NCCL work: drop them before tearing the communicator down, and leave
+    # through os._exit so a stuck communicator destructor can never hang the box
+    par._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
