@@ -148,3 +148,27 @@ def test_full_size_chunks_vs_oracle():
         kerr.append((rel_l2(k, okv[l]["k"]), rel_l2(v, okv[l]["v"])))
     print("cache K/V rel-L2 (layers 0, 14, 29):", kerr)
     assert max(max(p) for p in kerr) < 3e-2
+
+
+def test_batch_of_two_streams_small_model():
+    """B = 2 through the model contract (the reference batches streams in one call): every batch
+    element must equal its own single-stream run, and match the oracle."""
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import SMALL_CFG
+    cfg = wo.WanConfig(**SMALL_CFG)
+    sd = wo.init_state_dict(cfg, seed=0)
+    model = _model_from(cfg, sd, use_graph=False)
+    oracle = wo.OracleModel(cfg, sd).to(DEV)
+    size = cfg.local_attn_size * cfg.frame_seqlen
+    kv, cc = wo.new_kv_cache(cfg, 2, size, DEV), wo.new_crossattn_cache(cfg, 2, DEV)
+    okv, occ = wo.new_kv_cache(cfg, 2, size, DEV), wo.new_crossattn_cache(cfg, 2, DEV)
+    ctx = torch.cat([wo.synth_prompt_embeds(cfg, 7, 9), wo.synth_prompt_embeds(cfg, 8, 12)]).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    for chunk in range(6):  # fills the 4-frame cache and rolls twice
+        x = torch.randn(2, 16, 1, 8, 12, generator=g).to(torch.bfloat16).to(DEV)
+        t = torch.tensor([[937.5], [625.0]], device=DEV)
+        a = model(x, t=t, context=ctx, kv_cache=kv, crossattn_cache=cc, current_start=chunk * cfg.frame_seqlen)
+        b = oracle.forward(x, t, ctx, okv, occ, chunk * cfg.frame_seqlen)
+        assert rel_l2(a, b) < 1e-2, (chunk, rel_l2(a, b))
+        assert rel_l2(a[1], b[1]) < 1e-2
+    assert int(kv[0]["global_end_index"].item()) == int(okv[0]["global_end_index"].item())
