@@ -224,6 +224,7 @@ def run_ours(args):
 
     model = CausalWanModel(local_attn_size=12, sink_size=3)
     synth.random_init_(model, seed=0)
+    model.fp8_linears = bool(args.fp8_linears)  # optional W8A8 path; the headline number is bf16
     model = model.to(dev).to(torch.bfloat16)
     gen = WanDiffusionWrapper(model=model, timestep_shift=5.0)
 
@@ -304,7 +305,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp8-e4m3 block linears, bf16 elsewhere" if args.fp8_linears else "bf16", "data": "synthetic",
         "config": {
             "workload": "configs[1]: 5 s single-prompt generation, 21 latent frames (7 chunks x 5 forwards) "
                         "at 832x480, frame sink 3 + local window 12, 4-step DMD, batch 1 per GPU",
@@ -336,6 +338,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp8-linears", action="store_true",
+                    help="optional W8A8 (e4m3) linears inside the blocks; not the headline configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -149,6 +149,24 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
                   void* stream);
 
+/* Optional FP8 linears (README.md:50 of the reference advertises "FP8 quantization" at 24.8 FPS but
+ * ships no code for it, reports.md:24,39).  W8A8 with e4m3 operands on tcgen05 kind::f8f6f4:
+ *   A8 [M,K] e4m3 with per-row scale a_scale[M] (dynamic, produced by llb_ln_modulate_fp8 /
+ *   llb_quant_rows_fp8), W8 [N,K] e4m3 with per-output-channel scale w_scale[N] (static);
+ *   out = epilogue(acc * a_scale[row] * w_scale[col] + bias), same epilogues as llb_gemm_bf16.
+ * Leading dimensions of the fp8 operands are in elements (= bytes). */
+int llb_gemm_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw,
+                 const float* w_scale, void* out, int64_t ldo, int M, int N, int K, int epilogue,
+                 const void* bias, const void* gate, int64_t ld_gate, int rows_per_gate, int gate_row0,
+                 const void* res, int64_t ld_res, void* stream);
+/* llb_ln_modulate whose result is quantised row-wise to e4m3 (scale = amax / 448) instead of stored as bf16 */
+int llb_ln_modulate_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, float* out_scale, int rows,
+                        int C, const void* shift, const void* scale, int64_t ld_mod, int rows_per_frame,
+                        int row0, const void* ln_w, const void* ln_b, float eps, void* stream);
+/* row-wise dynamic e4m3 quantisation of a bf16 matrix [rows, C] */
+int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, float* out_scale, int rows,
+                       int C, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense attention  out = softmax(Q K^T * scale) V  per head (head_dim 128), flash-style with S/P/O
  * in TMEM.  Replaces attention()/flash_attention() (wan/modules/attention.py:43-197) at

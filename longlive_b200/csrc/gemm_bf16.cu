@@ -54,6 +54,8 @@ struct GemmParams {
   const __nv_bfloat16* res;
   int64_t ld_res;
   int num_m_tiles, num_n_tiles;
+  const float* a_scale;  // fp8 path: per-row activation scale [M]
+  const float* w_scale;  // fp8 path: per-output-channel weight scale [N]
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -66,7 +68,10 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-template <int BN>
+// kFp8: A and W are e4m3 bytes (K-block = 128 elements = the same 128-byte swizzle row), the MMA is
+// kind::f8f6f4 (K = 32 per instruction, twice the bf16 rate) and the epilogue applies
+// a_scale[row] * w_scale[col] before the bias.
+template <int BN, bool kFp8>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -93,7 +98,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = (p.K + kBK - 1) / kBK;
+  constexpr int kKElems = kFp8 ? 128 : kBK;  // elements per k-block (always 128 bytes)
+  const int num_kb = (p.K + kKElems - 1) / kKElems;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -130,8 +136,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kStageA;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_idx * kBM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n_idx * BN);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kKElems, m_idx * kBM);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kKElems, n_idx * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -139,7 +145,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // Whole warp in the loop (so descriptors stay in uniform registers); one elected lane issues.
-    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    constexpr uint32_t idesc = kFp8 ? umma_idesc_e4m3(kBM, BN) : umma_idesc_bf16(kBM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -161,7 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the
             // (addr >> 4) field of the descriptor
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (kFp8) umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
@@ -199,6 +206,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         // phase 1: thread == row.  bias (+activation) -> bf16 -> staging row (128 bytes)
         uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * 144);
+        float row_scale = 1.0f;
+        if constexpr (kFp8) {
+          const int grow_s = m_idx * kBM + q * 32 + lane;
+          row_scale = grow_s < p.M ? __ldg(p.a_scale + grow_s) : 0.f;
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           uint32_t packed[4];
@@ -210,8 +222,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;  // column inside the 64-wide chunk
-            const float a0 = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-            const float a1 = __uint_as_float(j + 1 < 32 ? v0[(j + 1) & 31] : v1[(j + 1) & 31]);
+            float a0 = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+            float a1 = __uint_as_float(j + 1 < 32 ? v0[(j + 1) & 31] : v1[(j + 1) & 31]);
+            if constexpr (kFp8) {
+              const int cj = col0 + j;
+              a0 *= row_scale * (cj < p.N ? __ldg(p.w_scale + cj) : 0.f);
+              a1 *= row_scale * (cj + 1 < p.N ? __ldg(p.w_scale + cj + 1) : 0.f);
+            }
             float y0 = a0 + bf16_lo(bb[e]), y1 = a1 + bf16_hi(bb[e]);
             if (epi == LLB_EPI_BIAS_GELU) {
               y0 = gelu_tanh_f(bf16_round(y0));
@@ -273,13 +290,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BN>
+template <int BN, bool kFp8>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kFp8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -287,22 +304,24 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, kFp8><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   LLB_LAUNCH_CHECK("gemm_bf16_kernel");
   return LLB_OK;
 }
 
 }  // namespace llb
 
-extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
-                             int64_t ldo, int M, int N, int K, int epilogue, const void* bias,
-                             const void* gate, int64_t ld_gate, int rows_per_gate, int gate_row0,
-                             const void* res, int64_t ld_res, void* stream) {
+static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
+                     int64_t ldo, int M, int N, int K, int epilogue, const void* bias, const void* gate,
+                     int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
+                     const float* a_scale, const float* w_scale, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(A && W && out, "gemm: null tensor");
   LLB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  LLB_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "gemm: K and N must be multiples of 8 (K=%d N=%d)", K, N);
-  LLB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "gemm: leading dims must be multiples of 8");
+  LLB_CHECK_ARG(K % (fp8 ? 16 : 8) == 0 && N % 8 == 0, "gemm: K / N alignment (K=%d N=%d)", K, N);
+  LLB_CHECK_ARG(lda % (fp8 ? 16 : 8) == 0 && ldw % (fp8 ? 16 : 8) == 0 && ldo % 8 == 0,
+                "gemm: leading dims must be 16-byte multiples");
+  LLB_CHECK_ARG(!fp8 || (a_scale && w_scale), "gemm_fp8: needs a_scale[M] and w_scale[N]");
   LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_RES, "gemm: unknown epilogue %d", epilogue);
   if (epilogue == LLB_EPI_BIAS_GATE_RES) {
     LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
@@ -341,17 +360,47 @@ extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t 
   p.res = static_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;
+  p.a_scale = a_scale;
+  p.w_scale = w_scale;
 
   CUtensorMap ta, tb;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (fp8) {
+    int rc = make_tmap_2d_u8(&ta, A, M, K, lda, kBM, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_u8(&tb, W, N, K, ldw, bn, 128);
+    if (rc) return rc;
+    switch (bn) {
+      case 64: return launch_gemm<64, true>(ta, tb, p, s);
+      case 128: return launch_gemm<128, true>(ta, tb, p, s);
+      case 192: return launch_gemm<192, true>(ta, tb, p, s);
+      default: return launch_gemm<256, true>(ta, tb, p, s);
+    }
+  }
   int rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBM, kBK);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, bn, kBK);
   if (rc) return rc;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch_gemm<64>(ta, tb, p, s);
-    case 128: return launch_gemm<128>(ta, tb, p, s);
-    case 192: return launch_gemm<192>(ta, tb, p, s);
-    default: return launch_gemm<256>(ta, tb, p, s);
+    case 64: return launch_gemm<64, false>(ta, tb, p, s);
+    case 128: return launch_gemm<128, false>(ta, tb, p, s);
+    case 192: return launch_gemm<192, false>(ta, tb, p, s);
+    default: return launch_gemm<256, false>(ta, tb, p, s);
   }
+}
+
+extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
+                             int64_t ldo, int M, int N, int K, int epilogue, const void* bias,
+                             const void* gate, int64_t ld_gate, int rows_per_gate, int gate_row0,
+                             const void* res, int64_t ld_res, void* stream) {
+  return gemm_impl(false, A, lda, W, ldw, out, ldo, M, N, K, epilogue, bias, gate, ld_gate, rows_per_gate,
+                   gate_row0, res, ld_res, nullptr, nullptr, stream);
+}
+
+extern "C" int llb_gemm_fp8(const void* A8, int64_t lda, const float* a_scale, const void* W8, int64_t ldw,
+                            const float* w_scale, void* out, int64_t ldo, int M, int N, int K, int epilogue,
+                            const void* bias, const void* gate, int64_t ld_gate, int rows_per_gate,
+                            int gate_row0, const void* res, int64_t ld_res, void* stream) {
+  return gemm_impl(true, A8, lda, W8, ldw, out, ldo, M, N, K, epilogue, bias, gate, ld_gate, rows_per_gate,
+                   gate_row0, res, ld_res, a_scale, w_scale, stream);
 }

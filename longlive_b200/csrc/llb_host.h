@@ -49,6 +49,10 @@ extern std::atomic<int64_t> g_launches;
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
+// Same for 1-byte elements (fp8): box_cols must be 128.
+int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols);
+
 int device_sm_count();
 
 }  // namespace llb

@@ -6,6 +6,7 @@
 #include "llb_common.cuh"
 #include "llb_host.h"
 
+#include <cuda_fp8.h>
 #include <string.h>
 
 namespace llb {
@@ -24,12 +25,43 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   modulate mode:  t = bf16(LN(x)); out = bf16(bf16(t * bf16(1 + scale)) + shift)
 //   affine mode:    out = bf16(LN(x) * w + b)                       (norm3, elementwise_affine)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// 8 bf16 (one uint4) * inv_scale -> 8 e4m3 bytes (one uint2), round-to-nearest, saturating
+__device__ __forceinline__ uint2 quant8_e4m3(const uint4& v, float inv_scale) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t r[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const unsigned short lo = __nv_cvt_float2_to_fp8x2(
+        make_float2(bf16_lo(w[2 * h]) * inv_scale, bf16_hi(w[2 * h]) * inv_scale), __NV_SATFINITE, __NV_E4M3);
+    const unsigned short hi = __nv_cvt_float2_to_fp8x2(
+        make_float2(bf16_lo(w[2 * h + 1]) * inv_scale, bf16_hi(w[2 * h + 1]) * inv_scale), __NV_SATFINITE, __NV_E4M3);
+    r[h] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+  }
+  return make_uint2(r[0], r[1]);
+}
+__device__ __forceinline__ float absmax8(const uint4& v) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  float m = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m = fmaxf(m, fmaxf(fabsf(bf16_lo(w[e])), fabsf(bf16_hi(w[e]))));
+  return m;
+}
+
+// kFp8Out: the modulated row is additionally quantised for the FP8 linear that consumes it:
+// per-row scale = amax / 448 (e4m3 max), out8 = round(y / scale); the bf16 output is skipped.
+template <bool kFp8Out>
 __global__ void __launch_bounds__(kRowWarps * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                    int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ shift,
                    const __nv_bfloat16* __restrict__ scale, int64_t ld_mod, int rows_per_frame,
                    int row0, const __nv_bfloat16* __restrict__ ln_w,
-                   const __nv_bfloat16* __restrict__ ln_b, float eps) {
+                   const __nv_bfloat16* __restrict__ ln_b, float eps, uint8_t* __restrict__ out8,
+                   int64_t ld8, float* __restrict__ out_scale) {
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -65,6 +97,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
   const bool affine = ln_w != nullptr;
   const int64_t mrow = static_cast<int64_t>((row0 + row) / rows_per_frame) * ld_mod;
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int vi = lane + i * 32;
@@ -95,9 +128,45 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
         }
         o[e] = pack_bf16x2(y0, y1);
       }
-      orow[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+      if constexpr (kFp8Out) {
+        v[i] = make_uint4(o[0], o[1], o[2], o[3]);  // keep the bf16-rounded result for the quant pass
+        amax = fmaxf(amax, absmax8(v[i]));
+      } else {
+        orow[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
+  if constexpr (kFp8Out) {
+    amax = warp_max(amax);
+    const float sc = amax > 0.f ? amax / 448.0f : 1.0f;
+    const float inv = 1.0f / sc;
+    uint2* o8 = reinterpret_cast<uint2*>(out8 + static_cast<int64_t>(row) * ld8);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) o8[vi] = quant8_e4m3(v[i], inv);
+    }
+    if (lane == 0) out_scale[row] = sc;
+  }
+}
+
+// Row-wise dynamic e4m3 quantisation of a bf16 matrix (any C % 8 == 0): two passes over the row.
+__global__ void __launch_bounds__(kRowWarps * 32)
+quant_rows_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* __restrict__ out8,
+                      int64_t ld8, float* __restrict__ out_scale, int rows, int C) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  float amax = 0.f;
+  for (int vi = lane; vi < nvec; vi += 32) amax = fmaxf(amax, absmax8(xr[vi]));
+  amax = warp_max(amax);
+  const float sc = amax > 0.f ? amax / 448.0f : 1.0f;
+  const float inv = 1.0f / sc;
+  uint2* o8 = reinterpret_cast<uint2*>(out8 + static_cast<int64_t>(row) * ld8);
+  for (int vi = lane; vi < nvec; vi += 32) o8[vi] = quant8_e4m3(xr[vi], inv);
+  if (lane == 0) out_scale[row] = sc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,12 +454,43 @@ extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ld
   LLB_CHECK_ARG(affine ? (ln_b != nullptr) : (shift && scale && rows_per_frame > 0),
                 "ln_modulate: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  ln_modulate_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  ln_modulate_kernel<false><<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
       rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
-      static_cast<const __nv_bfloat16*>(ln_b), eps);
+      static_cast<const __nv_bfloat16*>(ln_b), eps, nullptr, 0, nullptr);
   LLB_LAUNCH_CHECK("ln_modulate_kernel");
+  return LLB_OK;
+}
+
+extern "C" int llb_ln_modulate_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, float* out_scale,
+                                   int rows, int C, const void* shift, const void* scale, int64_t ld_mod,
+                                   int rows_per_frame, int row0, const void* ln_w, const void* ln_b,
+                                   float eps, void* stream) {
+  LLB_CHECK_ARG(x && out8 && out_scale && rows > 0, "ln_modulate_fp8: null tensor / no rows");
+  LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "ln_modulate_fp8: C=%d unsupported", C);
+  LLB_CHECK_ARG(ldx % 8 == 0 && ld8 % 16 == 0 && ld_mod % 8 == 0, "ln_modulate_fp8: leading dims");
+  const bool affine = ln_w != nullptr;
+  LLB_CHECK_ARG(affine ? (ln_b != nullptr) : (shift && scale && rows_per_frame > 0),
+                "ln_modulate_fp8: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;
+  ln_modulate_kernel<true><<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, nullptr, 0, rows, C,
+      static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
+      rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
+      static_cast<const __nv_bfloat16*>(ln_b), eps, static_cast<uint8_t*>(out8), ld8, out_scale);
+  LLB_LAUNCH_CHECK("ln_modulate_kernel<fp8>");
+  return LLB_OK;
+}
+
+extern "C" int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, float* out_scale,
+                                  int rows, int C, void* stream) {
+  LLB_CHECK_ARG(x && out8 && out_scale && rows > 0 && C > 0 && C % 8 == 0, "quant_rows_fp8: bad arguments");
+  LLB_CHECK_ARG(ldx % 8 == 0 && ld8 % 16 == 0, "quant_rows_fp8: leading dims");
+  const int grid = (rows + kRowWarps - 1) / kRowWarps;
+  quant_rows_fp8_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out8), ld8, out_scale, rows, C);
+  LLB_LAUNCH_CHECK("quant_rows_fp8_kernel");
   return LLB_OK;
 }
 

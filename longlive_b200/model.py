@@ -137,6 +137,9 @@ class CausalWanModel(nn.Module):
 
         self.use_cuda_graph = True
         self.attn_variant = 0
+        # optional W8A8 (e4m3) linears inside the blocks (q/k/v, o, cross q/o, ffn); set before the
+        # first forward or call refresh_weights() afterwards
+        self.fp8_linears = False
         self._packed = None           # fused / packed weights
         self._bufs: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, dict] = {}
@@ -151,6 +154,10 @@ class CausalWanModel(nn.Module):
         """The reference builds a flex-attention BlockMask here (causal_model.py:647-701) that the
         KV-cache path never reads; kept as a no-op for call compatibility."""
         return None
+
+    def refresh_weights(self):
+        """Drop packed weights, workspaces and captured graphs (after editing parameters / flags)."""
+        self._packed, self._bufs, self._graphs = None, {}, {}
 
     def _apply(self, fn, *a, **k):  # weights moved / cast -> repack lazily
         self._packed, self._bufs, self._graphs = None, {}, {}
@@ -191,6 +198,10 @@ class CausalWanModel(nn.Module):
                 "f1_w": c(blk.ffn[0].weight), "f1_b": c(blk.ffn[0].bias),
                 "f2_w": c(blk.ffn[2].weight), "f2_b": c(blk.ffn[2].bias),
             })
+        if self.fp8_linears:
+            for lw in P["layers"]:
+                for nm in ("qkv", "o", "cq", "co", "f1", "f2"):
+                    lw[nm + "_w8"], lw[nm + "_ws"] = ops.quantize_weight_e4m3(lw[nm + "_w"])
         P["mod_all"] = c(torch.stack([b.modulation.reshape(-1) for b in self.blocks], 0))  # [Lyr, 6C]
         P["head_mod"] = c(self.head.modulation.reshape(1, -1))                             # [1, 2C]
         P["head_w"], P["head_b"] = c(self.head.head.weight), c(self.head.head.bias)
@@ -217,6 +228,12 @@ class CausalWanModel(nn.Module):
                 "hmod": e(1, B * F, 2 * C_), "y": e(R, self.out_dim * 4), "out": e(B, self.out_dim, F, H, W),
                 "params": torch.zeros(STEP_PARAMS_INT32, dtype=torch.int32, device=dev),
             }
+            if self.fp8_linears:
+                self._bufs[key].update({
+                    "a8": torch.empty(R, C_, dtype=torch.uint8, device=dev),
+                    "h8": torch.empty(R, Cf, dtype=torch.uint8, device=dev),
+                    "sa": torch.empty(R, dtype=torch.float32, device=dev),
+                })
         return self._bufs[key]
 
     # ------------------------------------------------------------------------------------------
@@ -295,11 +312,27 @@ class CausalWanModel(nn.Module):
         ops.gemm(b["es"], P["tproj_w"], P["tproj_b"], out=b["e0"])
         ops.modulation_table(P["mod_all"], b["e0"], out=b["mod"])
         x, xm = b["x"], b["xm"]
+        f8 = self.fp8_linears
+
+        def lin(name, lw, a, **kw):
+            """One block Linear: bf16 tcgen05 GEMM, or W8A8 (a = (a8, scale)) when fp8_linears."""
+            if f8:
+                return ops.gemm_fp8(a[0], a[1], lw[name + "_w8"], lw[name + "_ws"], lw[name + "_b"], **kw)
+            return ops.gemm(a, lw[name + "_w"], lw[name + "_b"], **kw)
+
+        def ln_in(**kw):
+            """LayerNorm(+modulate) producing the next Linear's input (bf16, or e4m3 + row scales)."""
+            if f8:
+                return ops.ln_modulate_fp8(x, b["a8"], b["sa"], eps=eps, **kw)
+            return ops.ln_modulate(x, eps=eps, out=xm, **kw)
+
+        def act_in(t, buf="a8"):
+            return ops.quant_rows_fp8(t, b[buf], b["sa"]) if f8 else t
+
         for i, lw in enumerate(P["layers"]):
             m = b["mod"][i]  # [B*F, 6C]
             e = [m[:, k * C_:(k + 1) * C_] for k in range(6)]
-            ops.ln_modulate(x, shift=e[0], scale=e[1], rows_per_frame=fs, eps=eps, out=xm)
-            ops.gemm(xm, lw["qkv_w"], lw["qkv_b"], out=b["qkv"])
+            lin("qkv", lw, ln_in(shift=e[0], scale=e[1], rows_per_frame=fs), out=b["qkv"])
             kc, vc = kv_cache[i]["k"], kv_cache[i]["v"]
             for bi in range(B):
                 rows = slice(bi * L, (bi + 1) * L)
@@ -307,21 +340,19 @@ class CausalWanModel(nn.Module):
                 ops.rmsnorm_rope_append(b["qkv"][rows], b["q"][rows], k2, v2, lw["nq"], lw["nk"], P["rope"],
                                         (gh, gw), b["params"], n_heads=nh, eps=eps)
                 ops.attention(b["q"][rows], k2, v2, b["params"], n_heads=nh, out=b["attn"][rows], variant=v)
-            ops.gemm(b["attn"], lw["o_w"], lw["o_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2],
-                     rows_per_gate=fs, res=x, out=x)
-            ops.ln_modulate(x, ln_w=lw["n3_w"], ln_b=lw["n3_b"], eps=eps, out=xm)
-            ops.gemm(xm, lw["cq_w"], lw["cq_b"], out=b["cq"])
+            lin("o", lw, act_in(b["attn"]), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2], rows_per_gate=fs,
+                res=x, out=x)
+            lin("cq", lw, ln_in(ln_w=lw["n3_w"], ln_b=lw["n3_b"]), out=b["cq"])
             ops.rmsnorm(b["cq"], lw["cnq"], eps, out=b["q"])
             ck, cv = crossattn_cache[i]["k"], crossattn_cache[i]["v"]
             for bi in range(B):
                 rows = slice(bi * L, (bi + 1) * L)
                 ops.attention(b["q"][rows], ck[bi].view(-1, C_), cv[bi].view(-1, C_), P["cross_segs"],
                               n_heads=nh, out=b["attn"][rows], variant=v)
-            ops.gemm(b["attn"], lw["co_w"], lw["co_b"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
-            ops.ln_modulate(x, shift=e[3], scale=e[4], rows_per_frame=fs, eps=eps, out=xm)
-            ops.gemm(xm, lw["f1_w"], lw["f1_b"], epilogue=ops.EPI_BIAS_GELU, out=b["h"])
-            ops.gemm(b["h"], lw["f2_w"], lw["f2_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5],
-                     rows_per_gate=fs, res=x, out=x)
+            lin("co", lw, act_in(b["attn"]), epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+            lin("f1", lw, ln_in(shift=e[3], scale=e[4], rows_per_frame=fs), epilogue=ops.EPI_BIAS_GELU, out=b["h"])
+            lin("f2", lw, act_in(b["h"], "h8"), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
+                res=x, out=x)
         # head (causal_model.py:497-508): modulation [1,2,C] + e [B,F,1,C]
         b["e2"][:, :C_].copy_(b["e"]); b["e2"][:, C_:].copy_(b["e"])
         ops.modulation_table(P["head_mod"], b["e2"], out=b["hmod"])

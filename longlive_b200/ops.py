@@ -16,7 +16,7 @@ from ._lib import (EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, EPI
                    STEP_PARAMS_INT32, StepParams)
 
 __all__ = [
-    "gemm", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
+    "gemm", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
     "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
     "build_rope_table", "launch_count",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES",
@@ -66,6 +66,67 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         rows_per_gate, gate_row0, _ptr(res), res.stride(0) if res is not None else 0, _stream())
     _lib.check(rc, "llb_gemm_bf16")
     return out
+
+
+def gemm_fp8(a8: torch.Tensor, a_scale: torch.Tensor, w8: torch.Tensor, w_scale: torch.Tensor,
+             bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
+             gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0, gate_row0: int = 0,
+             res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """W8A8 linear: a8 [M,K] / w8 [N,K] e4m3 (torch.float8_e4m3fn or uint8 storage), a_scale [M] and
+    w_scale [N] float32; out bf16 [M,N] = epilogue(acc * a_scale[:,None] * w_scale[None,:] + bias)."""
+    for t, n in ((a8, "a8"), (w8, "w8")):
+        if not t.is_cuda or t.element_size() != 1 or t.stride(-1) != 1:
+            raise RuntimeError(f"{n}: expected a 1-byte CUDA tensor with contiguous rows")
+    _req(a_scale, "a_scale", torch.float32); _req(w_scale, "w_scale", torch.float32)
+    M, K = a8.shape
+    N, K2 = w8.shape
+    assert K == K2 and a_scale.numel() == M and w_scale.numel() == N
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a8.device)
+    rc = _lib.lib().llb_gemm_fp8(
+        a8.data_ptr(), a8.stride(0), a_scale.data_ptr(), w8.data_ptr(), w8.stride(0), w_scale.data_ptr(),
+        out.data_ptr(), out.stride(0), M, N, K, epilogue, _ptr(bias), _ptr(gate),
+        gate.stride(0) if gate is not None else 0, rows_per_gate, gate_row0, _ptr(res),
+        res.stride(0) if res is not None else 0, _stream())
+    _lib.check(rc, "llb_gemm_fp8")
+    return out
+
+
+def quant_rows_fp8(x: torch.Tensor, out8: Optional[torch.Tensor] = None,
+                   out_scale: Optional[torch.Tensor] = None):
+    """bf16 [rows, C] -> (e4m3 bytes [rows, C] as uint8, float32 scale [rows])."""
+    _req(x, "x")
+    rows, Cc = x.shape
+    if out8 is None:
+        out8 = torch.empty((rows, Cc), dtype=torch.uint8, device=x.device)
+    if out_scale is None:
+        out_scale = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rc = _lib.lib().llb_quant_rows_fp8(x.data_ptr(), x.stride(0), out8.data_ptr(), out8.stride(0),
+                                       out_scale.data_ptr(), rows, Cc, _stream())
+    _lib.check(rc, "llb_quant_rows_fp8")
+    return out8, out_scale
+
+
+def ln_modulate_fp8(x: torch.Tensor, out8: torch.Tensor, out_scale: torch.Tensor, *,
+                    shift: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+                    rows_per_frame: int = 0, row0: int = 0, ln_w: Optional[torch.Tensor] = None,
+                    ln_b: Optional[torch.Tensor] = None, eps: float = 1e-6):
+    _req(x, "x")
+    rows, Cc = x.shape
+    ld_mod = shift.stride(0) if shift is not None else 0
+    rc = _lib.lib().llb_ln_modulate_fp8(
+        x.data_ptr(), x.stride(0), out8.data_ptr(), out8.stride(0), out_scale.data_ptr(), rows, Cc,
+        _ptr(shift), _ptr(scale), ld_mod, rows_per_frame, row0, _ptr(ln_w), _ptr(ln_b), C.c_float(eps), _stream())
+    _lib.check(rc, "llb_ln_modulate_fp8")
+    return out8, out_scale
+
+
+def quantize_weight_e4m3(w: torch.Tensor):
+    """Static per-output-channel e4m3 quantisation of a Linear weight [N, K] (done once at load time)."""
+    wf = w.float()
+    sc = (wf.abs().amax(dim=1).clamp_min(1e-12) / 448.0)
+    w8 = (wf / sc[:, None]).to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+    return w8, sc.to(torch.float32).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -61,6 +61,14 @@ def main():
                       "tflops": fl / ms / 1e9})
             except Exception as e:  # keep going: this is a bring-up tool
                 emit({"kernel": "llb_gemm_bf16", "shape": [M, N, K], "error": str(e)[:200]})
+            try:
+                a8, sa = ops.quant_rows_fp8(a)
+                w8, sw = ops.quantize_weight_e4m3(w)
+                ms = timeit(lambda: ops.gemm_fp8(a8, sa, w8, sw, b, out=out), iters=args.iters)
+                emit({"kernel": "llb_gemm_fp8", "shape": [M, N, K], "name": name, "ms": ms,
+                      "tflops": fl / ms / 1e9})
+            except Exception as e:
+                emit({"kernel": "llb_gemm_fp8", "shape": [M, N, K], "error": str(e)[:200]})
             ms = timeit(lambda: torch.addmm(b, a, w.t(), out=out), iters=args.iters)
             emit({"kernel": "cublas_addmm", "shape": [M, N, K], "name": name, "ms": ms,
                   "tflops": fl / ms / 1e9})
