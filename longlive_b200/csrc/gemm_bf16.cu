@@ -37,8 +37,11 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   // TMEM allocations are powers of two >= 32 columns; two accumulator stages of BN columns each
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kEpiVecBytesPerWarp = 2 * BN * 4;  // per-warp fp32 bias[BN] and w_scale[BN]
   static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + 4 * kEpiStageBytesPerWarp + 256 /*barriers*/;
+      1024 /*align slack*/ + kStages * kStageBytes + 4 * (kEpiStageBytesPerWarp + kEpiVecBytesPerWarp) +
+      256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 };
 
 struct GemmParams {
@@ -84,7 +87,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t stage_base = smem_base;
   const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
   uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
-  const uint32_t bar_base = epi_base + 4 * kEpiStageBytesPerWarp;
+  const uint32_t bar_base = epi_base + 4 * (kEpiStageBytesPerWarp + Cfg::kEpiVecBytesPerWarp);
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -92,7 +95,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(epi_gen + 4 * kEpiStageBytesPerWarp +
+      reinterpret_cast<volatile uint32_t*>(epi_gen + 4 * (kEpiStageBytesPerWarp + Cfg::kEpiVecBytesPerWarp) +
                                            8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
@@ -181,6 +184,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     uint8_t* my_stage = epi_gen + (warp - 2) * kEpiStageBytesPerWarp;
+    float* my_bias =
+        reinterpret_cast<float*>(epi_gen + 4 * kEpiStageBytesPerWarp + (warp - 2) * Cfg::kEpiVecBytesPerWarp);
+    float* my_ws = my_bias + BN;
     const int epi = p.epilogue;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -188,6 +194,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_idx = tile / p.num_m_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      // Stage this tile's bias (and fp8 weight scales) as fp32 in shared memory while the main loop
+      // is still running: the per-column values are then broadcast LDS reads instead of global loads
+      // whose latency a single epilogue warp per scheduler cannot hide.
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int cl = lane + i * 32, cg = n_idx * BN + cl;
+        my_bias[cl] = (p.bias != nullptr && cg < p.N) ? __bfloat162float(p.bias[cg]) : 0.f;
+        if constexpr (kFp8) my_ws[cl] = cg < p.N ? __ldg(p.w_scale + cg) : 0.f;
+      }
+      __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
@@ -214,22 +230,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           uint32_t packed[4];
-          // 8 bias values for columns col0 + 8g .. +7 (same address across the warp: broadcast)
-          uint4 bvec = make_uint4(0, 0, 0, 0);
-          if (p.bias != nullptr && col0 + g * 8 < p.N)
-            bvec = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + g * 8));
-          const uint32_t* bb = reinterpret_cast<const uint32_t*>(&bvec);
+          // 8 bias values (and fp8 scales) for columns col0 + 8g .. +7: broadcast LDS
+          const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c * 64 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c * 64 + g * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float ws[8];
+          if constexpr (kFp8) {
+            const float4 w0 = *reinterpret_cast<const float4*>(my_ws + c * 64 + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(my_ws + c * 64 + g * 8 + 4);
+            ws[0] = w0.x * row_scale; ws[1] = w0.y * row_scale; ws[2] = w0.z * row_scale; ws[3] = w0.w * row_scale;
+            ws[4] = w1.x * row_scale; ws[5] = w1.y * row_scale; ws[6] = w1.z * row_scale; ws[7] = w1.w * row_scale;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = g * 8 + e * 2;  // column inside the 64-wide chunk
             float a0 = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
             float a1 = __uint_as_float(j + 1 < 32 ? v0[(j + 1) & 31] : v1[(j + 1) & 31]);
             if constexpr (kFp8) {
-              const int cj = col0 + j;
-              a0 *= row_scale * (cj < p.N ? __ldg(p.w_scale + cj) : 0.f);
-              a1 *= row_scale * (cj + 1 < p.N ? __ldg(p.w_scale + cj + 1) : 0.f);
+              a0 *= ws[2 * e];
+              a1 *= ws[2 * e + 1];
             }
-            float y0 = a0 + bf16_lo(bb[e]), y1 = a1 + bf16_hi(bb[e]);
+            float y0 = a0 + bb[2 * e], y1 = a1 + bb[2 * e + 1];
             if (epi == LLB_EPI_BIAS_GELU) {
               y0 = gelu_tanh_f(bf16_round(y0));
               y1 = gelu_tanh_f(bf16_round(y1));
@@ -242,39 +263,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           srow[g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         __syncwarp();
-        // phase 2: 8 lanes cover one 128-byte row segment -> coalesced global traffic
+        // phase 2: 8 lanes cover one 128-byte row segment -> coalesced global traffic.  Loads of
+        // the residual / gate for four rows are issued together before any arithmetic so their
+        // latency overlaps (one epilogue warp per scheduler has nobody else to hide it).
         const int seg = lane & 7;
         const int gcol = col0 + seg * 8;
+        const bool col_ok = gcol < p.N;
+        const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES);
+        const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + (lane >> 3);
-          const int grow = m_idx * kBM + q * 32 + r;
-          if (grow < p.M && gcol < p.N) {
-            uint4 y = *reinterpret_cast<const uint4*>(my_stage + r * 144 + seg * 16);
-            if (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES) {
-              const uint4 x =
-                  *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(grow) * p.ld_res + gcol);
-              uint4 gt = make_uint4(0, 0, 0, 0);
-              if (epi == LLB_EPI_BIAS_GATE_RES) {
-                gt = __ldg(reinterpret_cast<const uint4*>(
+        for (int half = 0; half < 2; ++half) {
+          uint4 yv[4], xv[4], gv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (half * 4 + i) * 4 + (lane >> 3);
+            const int grow = m_idx * kBM + q * 32 + r;
+            yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 144 + seg * 16);
+            xv[i] = make_uint4(0, 0, 0, 0);
+            gv[i] = make_uint4(0, 0, 0, 0);
+            if (grow < p.M && col_ok) {
+              if (has_res)
+                xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(grow) * p.ld_res + gcol);
+              if (has_gate)
+                gv[i] = __ldg(reinterpret_cast<const uint4*>(
                     p.gate + static_cast<int64_t>((grow + p.gate_row0) / p.rows_per_gate) * p.ld_gate + gcol));
-              }
-              const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
-              const uint32_t* xx = reinterpret_cast<const uint32_t*>(&x);
-              const uint32_t* gg = reinterpret_cast<const uint32_t*>(&gt);
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float y0 = bf16_lo(yy[e]), y1 = bf16_hi(yy[e]);
-                if (epi == LLB_EPI_BIAS_GATE_RES) {
-                  y0 = bf16_round(y0 * bf16_lo(gg[e]));
-                  y1 = bf16_round(y1 * bf16_hi(gg[e]));
-                }
-                o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
-              }
-              y = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + gcol) = y;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (half * 4 + i) * 4 + (lane >> 3);
+            const int grow = m_idx * kBM + q * 32 + r;
+            if (grow < p.M && col_ok) {
+              uint4 y = yv[i];
+              if (has_res) {
+                const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yv[i]);
+                const uint32_t* xx = reinterpret_cast<const uint32_t*>(&xv[i]);
+                const uint32_t* gg = reinterpret_cast<const uint32_t*>(&gv[i]);
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float y0 = bf16_lo(yy[e]), y1 = bf16_hi(yy[e]);
+                  if (has_gate) {
+                    y0 = bf16_round(y0 * bf16_lo(gg[e]));
+                    y1 = bf16_round(y1 * bf16_hi(gg[e]));
+                  }
+                  o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
+                }
+                y = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+              *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + gcol) = y;
+            }
           }
         }
         __syncwarp();
@@ -321,7 +359,8 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   LLB_CHECK_ARG(K % (fp8 ? 16 : 8) == 0 && N % 8 == 0, "gemm: K / N alignment (K=%d N=%d)", K, N);
   LLB_CHECK_ARG(lda % (fp8 ? 16 : 8) == 0 && ldw % (fp8 ? 16 : 8) == 0 && ldo % 8 == 0,
                 "gemm: leading dims must be 16-byte multiples");
-  LLB_CHECK_ARG(!fp8 || (a_scale && w_scale), "gemm_fp8: needs a_scale[M] and w_scale[N]");
+  LLB_CHECK_ARG(!fp8 || (a_scale && w_scale && (reinterpret_cast<uintptr_t>(w_scale) & 15) == 0),
+                "gemm_fp8: needs a_scale[M] and a 16-byte aligned w_scale[N]");
   LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_RES, "gemm: unknown epilogue %d", epilogue);
   if (epilogue == LLB_EPI_BIAS_GATE_RES) {
     LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
