@@ -446,7 +446,3 @@ class CausalWanModel(nn.Module):
             for c in kv_cache:
                 c["global_end_index"].fill_(ring.global_end)
                 c["local_end_index"].fill_(ring.local_end)
-
-    # convenience for tests
-    def kernels_per_forward(self, B: int = 1) -> int:
-        return 7 + self.num_layers * (9 + 4 * B) + 6 + 2 * B

@@ -159,10 +159,12 @@ _ATTN_WS = {}
 
 
 def attention_workspace(device) -> torch.Tensor:
-    """Per-device scratch of llb_attn_fwd's stream-K split (zeroed once; flags are self-resetting).
-    One buffer per device is enough because launches on a stream are serialised."""
+    """Scratch of llb_attn_fwd's split-remainder scheduling (zeroed once; flags are self-resetting).
+    One buffer per (device, stream): launches on one stream are serialised, launches on different
+    streams must not share partials.  A graph-capture stream gets (and keeps) its own buffer."""
     dev = torch.device(device)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     ws = _ATTN_WS.get(key)
     if ws is None:
         n = int(_lib.lib().llb_attn_workspace_bytes())
