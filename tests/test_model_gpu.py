@@ -172,3 +172,55 @@ def test_batch_of_two_streams_small_model():
         assert rel_l2(a, b) < 1e-2, (chunk, rel_l2(a, b))
         assert rel_l2(a[1], b[1]) < 1e-2
     assert int(kv[0]["global_end_index"].item()) == int(okv[0]["global_end_index"].item())
+
+
+EDGE_CONFIGS = [
+    # name, local_attn, sink, cache_frames, max_attention_frames, chunk_frames, n_chunks
+    ("chunk1_sink3_zero_sink_rows", 6, 3, 6, 6, 1, 9),    # first calls attend still-empty (zero) sink rows
+    ("global_attention", -1, 0, 8, None, 2, 4),            # local_attn_size = -1: never rolls
+    ("cache_larger_than_window", 4, 1, 8, 4, 1, 10),       # training-style caller: size > window -> 2 segments
+    ("no_sink_window3", 3, 0, 3, 3, 1, 7),                 # sink_size = 0 branch (causal_model.py:354-360)
+]
+
+
+@pytest.mark.parametrize("name,local,sink,cache_frames,max_frames,chunk,n_chunks", EDGE_CONFIGS,
+                         ids=[c[0] for c in EDGE_CONFIGS])
+def test_edge_cache_configurations_vs_oracle(name, local, sink, cache_frames, max_frames, chunk, n_chunks):
+    """Unusual but reference-legal cache geometries on the small model, 2 calls per chunk
+    (first write + recompute), CUDA path vs oracle: outputs, indices and logical cache content."""
+    import dataclasses
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import SMALL_CFG
+    from longlive_b200.kv_ring import logical_view
+    cfg = wo.WanConfig(**{**SMALL_CFG, "local_attn_size": local, "sink_size": sink})
+    sd = wo.init_state_dict(cfg, seed=0)
+    fs = cfg.frame_seqlen
+    model = _model_from(cfg, sd, use_graph=False)
+    oracle = wo.OracleModel(cfg, sd).to(DEV)
+    if max_frames is not None:  # what _set_all_modules_max_attention_size does
+        for mod in model.modules():
+            if hasattr(mod, "max_attention_size"):
+                mod.max_attention_size = max_frames * fs
+        oracle.cfg = dataclasses.replace(cfg)
+        object.__setattr__(oracle.cfg, "_max_override", max_frames * fs)
+    size = cache_frames * fs
+    kv, cc = wo.new_kv_cache(cfg, 1, size, DEV), wo.new_crossattn_cache(cfg, 1, DEV)
+    okv, occ = wo.new_kv_cache(cfg, 1, size, DEV), wo.new_crossattn_cache(cfg, 1, DEV)
+    ctx = wo.synth_prompt_embeds(cfg, 3, 9).to(DEV)
+    g = torch.Generator().manual_seed(11)
+    worst = 0.0
+    for c in range(n_chunks):
+        for t in (937.5, 0.0):
+            x = torch.randn(1, 16, chunk, 8, 12, generator=g).to(torch.bfloat16).to(DEV)
+            tt = torch.full((1, chunk), t, device=DEV)
+            a = model(x, t=tt, context=ctx, kv_cache=kv, crossattn_cache=cc, current_start=c * chunk * fs)
+            b = oracle.forward(x, tt, ctx, okv, occ, c * chunk * fs)
+            worst = max(worst, rel_l2(a, b))
+    assert worst < 1e-2, (name, worst)
+    ring = kv[0]["_llb_ring"]
+    assert ring.global_end == int(okv[0]["global_end_index"].item())
+    assert ring.local_end == int(okv[0]["local_end_index"].item())
+    le = ring.local_end
+    for l in range(cfg.num_layers):
+        k, v = logical_view(kv[l], ring)
+        assert rel_l2(k[:, :le], okv[l]["k"][:, :le]) < 1e-2 and rel_l2(v[:, :le], okv[l]["v"][:, :le]) < 1e-2
