@@ -79,6 +79,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA/ALU pipes for a pair of values (FA4-style MUFU offload): t = j + r with j = round(t)
+// taken from the low mantissa bits of t + 1.5*2^23, 2^r by a degree-3 polynomial on [-0.5, 0.5]
+// (max relative error 1.6e-4, far below the bf16 rounding of P), and 2^j added into the exponent.
+__device__ __forceinline__ float2 exp2_poly2(float2 t) {
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 u = __fadd2_rn(t, magic);
+  const float2 j = __fadd2_rn(u, make_float2(-12582912.0f, -12582912.0f));
+  const float2 r = __ffma2_rn(j, make_float2(-1.0f, -1.0f), t);
+  float2 q = __ffma2_rn(r, make_float2(0.05676588788628578f, 0.05676588788628578f),
+                        make_float2(0.24273726344108582f, 0.24273726344108582f));
+  q = __ffma2_rn(q, r, make_float2(0.6929193139076233f, 0.6929193139076233f));
+  q = __ffma2_rn(q, r, make_float2(0.9999317526817322f, 0.9999317526817322f));
+  q.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(u.x) << 23));
+  q.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(u.y) << 23));
+  return q;
+}
+
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -210,7 +229,10 @@ struct SegIter {
   }
 };
 
-template <bool kPTmem>
+// kPoly: every kPoly-th pair of probabilities is exponentiated with exp2_poly2 instead of MUFU
+// (0 = MUFU only).  MUFU.EX2 runs at 16/clk/SM, exactly the rate the two S tiles are produced at, so
+// moving a quarter of the work to the FMA pipe takes the special-function unit off the critical path.
+template <bool kPTmem, int kPoly>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -521,17 +543,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           m_used = m_new;
         }
         const float neg = -m_used * c;
-        float l0 = 0.f, l1 = 0.f;
+        const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * i]), c, neg));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * i + 1]), c, neg));
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_bf16x2(p0, p1);
+            const float2 tt = __ffma2_rn(
+                make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
+            float2 pp;
+            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
+              pp = exp2_poly2(tt);
+            } else {
+              pp.x = ex2_approx(tt.x);
+              pp.y = ex2_approx(tt.y);
+            }
+            if (i & 1) lb = __fadd2_rn(lb, pp);
+            else la = __fadd2_rn(la, pp);
+            pk[i] = pack_bf16x2(pp.x, pp.y);
           }
           if constexpr (kPTmem) {
             tmem_st16(t_s + cc * 16, pk);
@@ -546,7 +576,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
           }
         }
-        l += l0 + l1;
+        la = __fadd2_rn(la, lb);
+        l += la.x + la.y;
         if constexpr (kPTmem) {
           tmem_wait_st();
         } else {
@@ -660,13 +691,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <bool kPTmem>
+template <bool kPTmem, int kPoly>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
   using Cfg = AttnCfg<kPTmem>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem>,
+    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -683,7 +714,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   cfg.attrs = attr;
   static const bool coop = getenv("LLB_ATTN_COOP") == nullptr || atoi(getenv("LLB_ATTN_COOP")) != 0;
   cfg.numAttrs = coop ? 1 : 0;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -743,6 +774,11 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     p.shard = *shard;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (variant == 1) return launch_attn<false>(tq, tk, tv, p, grid, s);
-  return launch_attn<true>(tq, tk, tv, p, grid, s);
+  // variant bit 0: P through shared memory instead of TMEM; bit 1: MUFU-only exp2 (no polynomial)
+  switch (variant & 3) {
+    case 1: return launch_attn<false, 4>(tq, tk, tv, p, grid, s);
+    case 2: return launch_attn<true, 0>(tq, tk, tv, p, grid, s);
+    case 3: return launch_attn<false, 0>(tq, tk, tv, p, grid, s);
+    default: return launch_attn<true, 4>(tq, tk, tv, p, grid, s);
+  }
 }
