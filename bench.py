@@ -39,6 +39,7 @@ T_FRAMES = 21  # configs[1]
 METRIC = "generated video FPS at 832x480 (denoising path, 4 video frames per latent frame)"
 UNIT = "frames/s"
 ATTN_FLOPS = 4.0 * 4680 * 18720 * 12 * 128  # steady-state self-attention launch
+PUBLISHED_FPS = 20.7  # per GPU, BASELINE.md section 1 (H100; the only published number for this metric)
 
 
 def _peaks():
@@ -305,7 +306,9 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": "weak",
+        # the reference's published 20.7 FPS (bf16, one H100; README.md:25,50)
+        "vs_baseline": value / (PUBLISHED_FPS * world),
         "dtype": "fp8-e4m3 block linears, bf16 elsewhere" if args.fp8_linears else "bf16", "data": "synthetic",
         "config": {
             "workload": "configs[1]: 5 s single-prompt generation, 21 latent frames (7 chunks x 5 forwards) "
@@ -316,7 +319,8 @@ def run_ours(args):
             "cuda_graph": bool(model.use_cuda_graph),
             "steady_state_video_fps": steady["video_fps_steady"] if steady else None,
             "steady_state_ms_per_latent_frame": steady["inter_frame_latency_ms"] if steady else None,
-            "published_h100_fps": 20.7,
+            "published_h100_fps": PUBLISHED_FPS,
+            "vs_baseline_note": "value / (20.7 FPS x n_gpus): published bf16 number on one H100 per stream",
         },
         "e2e": {"value": e2e, "unit": UNIT,
                 "h2d_bytes_per_step": noise_host.numel() * 2 + embeds_host.numel() * 2,

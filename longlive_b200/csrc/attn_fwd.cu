@@ -255,9 +255,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto ofree_bar = [&](int s) { return bar_base + 8u * (10 + s); };
   auto kvfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
   auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (12 + 2 * kStages);
+  auto sfree_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (12 + 2 * kStages));
+      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -273,6 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
       mbar_init(ofree_bar(s), 4);
+      mbar_init(sfree_bar(s), 4);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
@@ -327,21 +329,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tma_load_2d(q_base + kTileBytes, &tmap_q, qfull_bar(1), col, q_row0 + 128);
             tma_load_2d(q_base + kTileBytes + kBoxBytes, &tmap_q, qfull_bar(1), col + 64, q_row0 + 128);
           }
+          auto load_tile = [&](const CUtensorMap* tm, int row0) {
+            mbar_wait(kvempty_bar(stage), phase ^ 1);
+            const uint32_t dst = kv_base + stage * kTileBytes;
+            mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
+            tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
+            tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          };
           kv_it.seek(sg.t0);
-          for (int j = sg.t0; j < sg.t1; ++j) {
-            int row0, valid;
-            kv_it.get(row0, valid);
-#pragma unroll
-            for (int kv = 0; kv < 2; ++kv) {
-              mbar_wait(kvempty_bar(stage), phase ^ 1);
-              const uint32_t dst = kv_base + stage * kTileBytes;
-              const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
-              mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
-              tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
-              tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+          int row0, valid;
+          if constexpr (kPTmem) {
+            // consumption order K_j, V_j, K_j+1, V_j+1, ...
+            for (int j = sg.t0; j < sg.t1; ++j) {
+              kv_it.get(row0, valid);
+              load_tile(&tmap_k, row0);
+              load_tile(&tmap_v, row0);
+              kv_it.next();
             }
-            kv_it.next();
+          } else {
+            // early-QK order: K_t0, then (K_j+1, V_j) pairs - S(j+1) is produced before P(j) is consumed
+            KvTileIter k_it = kv_it;
+            k_it.get(row0, valid);
+            load_tile(&tmap_k, row0);
+            k_it.next();
+            for (int j = sg.t0; j < sg.t1; ++j) {
+              if (j + 1 < sg.t1) {
+                k_it.get(row0, valid);
+                load_tile(&tmap_k, row0);
+                k_it.next();
+              }
+              kv_it.get(row0, valid);
+              load_tile(&tmap_v, row0);
+              kv_it.next();
+            }
           }
         }
       }
@@ -382,92 +403,196 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
         uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
 
-        for (; sg.ok; sg.next()) {
-          const int head = sg.item / p.n_pairs;
-          const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-          const bool has1 = q_row0 + 128 < p.Lq;
-          const int nt = sg.t1 - sg.t0;
-          // prologue: S_t(first) = Q_t K^T
-          mbar_wait(qfull_bar(0), qph0);
-          qph0 ^= 1;
-          if (has1) {
-            mbar_wait(qfull_bar(1), qph1);
-            qph1 ^= 1;
-          }
-          mbar_wait(kvfull_bar(stage), phase);
-          tc_fence_after();
-          uint32_t kst = kv_base + stage * kTileBytes;
-          if (elect_one()) {
-            issue_qk(0, kst);
-            umma_commit(sfull_bar(0));
-            if (nt == 1) umma_commit(qempty_bar(0));
+        if constexpr (kPTmem) {
+          for (; sg.ok; sg.next()) {
+            const int head = sg.item / p.n_pairs;
+            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+            const bool has1 = q_row0 + 128 < p.Lq;
+            const int nt = sg.t1 - sg.t0;
+            // prologue: S_t(first) = Q_t K^T
+            mbar_wait(qfull_bar(0), qph0);
+            qph0 ^= 1;
             if (has1) {
-              issue_qk(1, kst);
-              umma_commit(sfull_bar(1));
-              if (nt == 1) umma_commit(qempty_bar(1));
+              mbar_wait(qfull_bar(1), qph1);
+              qph1 ^= 1;
             }
-            umma_commit(kvempty_bar(stage));
-          }
-          __syncwarp();
-          advance();
-          // O_t of the previous segment must have been drained by its softmax warps before the
-          // first PV of this segment overwrites it
-          mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
-          oseg0++;
-          if (has1) {
-            mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
-            oseg1++;
-          }
-          for (int j = 0; j < nt; ++j) {
-            const bool more = j + 1 < nt;
-            const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
-            // V_j
-            const int vstage = stage;
             mbar_wait(kvfull_bar(stage), phase);
-            const uint32_t vst = kv_base + stage * kTileBytes;
-            advance();
-            // K_{j+1}
-            int kstage = 0;
-            if (more) {
-              kstage = stage;
-              mbar_wait(kvfull_bar(stage), phase);
-              kst = kv_base + stage * kTileBytes;
-              advance();
-            }
-            // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
-            mbar_wait(pfull_bar(0), pcnt0 & 1);
-            pcnt0++;
             tc_fence_after();
+            uint32_t kst = kv_base + stage * kTileBytes;
             if (elect_one()) {
-              issue_pv(0, vst, j == 0);
-              umma_commit(odone_bar(0));
-              if (more) {
-                issue_qk(0, kst);
-                umma_commit(sfull_bar(0));
-                if (last_qk) umma_commit(qempty_bar(0));
+              issue_qk(0, kst);
+              umma_commit(sfull_bar(0));
+              if (nt == 1) umma_commit(qempty_bar(0));
+              if (has1) {
+                issue_qk(1, kst);
+                umma_commit(sfull_bar(1));
+                if (nt == 1) umma_commit(qempty_bar(1));
               }
-              if (!has1) {
-                umma_commit(kvempty_bar(vstage));
-                if (more) umma_commit(kvempty_bar(kstage));
-              }
+              umma_commit(kvempty_bar(stage));
             }
             __syncwarp();
+            advance();
+            // O_t of the previous segment must have been drained by its softmax warps before the
+            // first PV of this segment overwrites it
+            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
+            oseg0++;
             if (has1) {
-              mbar_wait(pfull_bar(1), pcnt1 & 1);
-              pcnt1++;
+              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
+              oseg1++;
+            }
+            for (int j = 0; j < nt; ++j) {
+              const bool more = j + 1 < nt;
+              const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
+              // V_j
+              const int vstage = stage;
+              mbar_wait(kvfull_bar(stage), phase);
+              const uint32_t vst = kv_base + stage * kTileBytes;
+              advance();
+              // K_{j+1}
+              int kstage = 0;
+              if (more) {
+                kstage = stage;
+                mbar_wait(kvfull_bar(stage), phase);
+                kst = kv_base + stage * kTileBytes;
+                advance();
+              }
+              // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
+              mbar_wait(pfull_bar(0), pcnt0 & 1);
+              pcnt0++;
               tc_fence_after();
               if (elect_one()) {
-                issue_pv(1, vst, j == 0);
-                umma_commit(odone_bar(1));
-                umma_commit(kvempty_bar(vstage));
+                issue_pv(0, vst, j == 0);
+                umma_commit(odone_bar(0));
                 if (more) {
-                  issue_qk(1, kst);
-                  umma_commit(sfull_bar(1));
-                  if (last_qk) umma_commit(qempty_bar(1));
-                  umma_commit(kvempty_bar(kstage));
+                  issue_qk(0, kst);
+                  umma_commit(sfull_bar(0));
+                  if (last_qk) umma_commit(qempty_bar(0));
+                }
+                if (!has1) {
+                  umma_commit(kvempty_bar(vstage));
+                  if (more) umma_commit(kvempty_bar(kstage));
                 }
               }
               __syncwarp();
+              if (has1) {
+                mbar_wait(pfull_bar(1), pcnt1 & 1);
+                pcnt1++;
+                tc_fence_after();
+                if (elect_one()) {
+                  issue_pv(1, vst, j == 0);
+                  umma_commit(odone_bar(1));
+                  umma_commit(kvempty_bar(vstage));
+                  if (more) {
+                    issue_qk(1, kst);
+                    umma_commit(sfull_bar(1));
+                    if (last_qk) umma_commit(qempty_bar(1));
+                    umma_commit(kvempty_bar(kstage));
+                  }
+                }
+                __syncwarp();
+              }
+            }
+          }
+        } else {
+          // Early-QK schedule (P staged in shared memory, so S and P do not alias): S_t(j+1) = Q_t K_j+1^T
+          // is issued as soon as the softmax warps have READ S_t(j) (s_free), before P_t(j) exists.
+          // The softmax warpgroups then find their next S tile ready and run back to back.
+          uint32_t qk0 = 0, qk1 = 0;  // QK groups issued per Q tile (s_free phase)
+          for (; sg.ok; sg.next()) {
+            const int head = sg.item / p.n_pairs;
+            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+            const bool has1 = q_row0 + 128 < p.Lq;
+            const int nt = sg.t1 - sg.t0;
+            mbar_wait(qfull_bar(0), qph0);
+            qph0 ^= 1;
+            if (has1) {
+              mbar_wait(qfull_bar(1), qph1);
+              qph1 ^= 1;
+            }
+            mbar_wait(kvfull_bar(stage), phase);
+            // S_t must have been read by the softmax warps of the previous segment's last tile
+            if (qk0 > 0) mbar_wait(sfree_bar(0), (qk0 - 1) & 1);
+            if (has1 && qk1 > 0) mbar_wait(sfree_bar(1), (qk1 - 1) & 1);
+            tc_fence_after();
+            uint32_t kst = kv_base + stage * kTileBytes;
+            if (elect_one()) {
+              issue_qk(0, kst);
+              umma_commit(sfull_bar(0));
+              if (nt == 1) umma_commit(qempty_bar(0));
+              if (has1) {
+                issue_qk(1, kst);
+                umma_commit(sfull_bar(1));
+                if (nt == 1) umma_commit(qempty_bar(1));
+              }
+              umma_commit(kvempty_bar(stage));
+            }
+            __syncwarp();
+            qk0++;
+            if (has1) qk1++;
+            advance();
+            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
+            oseg0++;
+            if (has1) {
+              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
+              oseg1++;
+            }
+            for (int j = 0; j < nt; ++j) {
+              const bool more = j + 1 < nt;
+              const bool last_qk = j + 2 == nt;
+              if (more) {
+                // K_{j+1}: S_t(j+1) as soon as S_t(j) has been read
+                const int kstage = stage;
+                mbar_wait(kvfull_bar(stage), phase);
+                kst = kv_base + stage * kTileBytes;
+                advance();
+                mbar_wait(sfree_bar(0), (qk0 - 1) & 1);
+                qk0++;
+                tc_fence_after();
+                if (elect_one()) {
+                  issue_qk(0, kst);
+                  umma_commit(sfull_bar(0));
+                  if (last_qk) umma_commit(qempty_bar(0));
+                  if (!has1) umma_commit(kvempty_bar(kstage));
+                }
+                __syncwarp();
+                if (has1) {
+                  mbar_wait(sfree_bar(1), (qk1 - 1) & 1);
+                  qk1++;
+                  tc_fence_after();
+                  if (elect_one()) {
+                    issue_qk(1, kst);
+                    umma_commit(sfull_bar(1));
+                    if (last_qk) umma_commit(qempty_bar(1));
+                    umma_commit(kvempty_bar(kstage));
+                  }
+                  __syncwarp();
+                }
+              }
+              // V_j: O_t += P_t(j) V_j
+              const int vstage = stage;
+              mbar_wait(kvfull_bar(stage), phase);
+              const uint32_t vst = kv_base + stage * kTileBytes;
+              advance();
+              mbar_wait(pfull_bar(0), pcnt0 & 1);
+              pcnt0++;
+              tc_fence_after();
+              if (elect_one()) {
+                issue_pv(0, vst, j == 0);
+                umma_commit(odone_bar(0));
+                if (!has1) umma_commit(kvempty_bar(vstage));
+              }
+              __syncwarp();
+              if (has1) {
+                mbar_wait(pfull_bar(1), pcnt1 & 1);
+                pcnt1++;
+                tc_fence_after();
+                if (elect_one()) {
+                  issue_pv(1, vst, j == 0);
+                  umma_commit(odone_bar(1));
+                  umma_commit(kvempty_bar(vstage));
+                }
+                __syncwarp();
+              }
             }
           }
         }
@@ -506,6 +631,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
         tmem_wait_ld();
+        bool prev_pv_done = kPTmem || j == sg.t0;  // TMEM-P: S_t(j) ready already implies PV_t(j-1) done
+        if constexpr (!kPTmem) {
+          // S_t(j) now lives in registers: let the MMA warp overwrite it with S_t(j+1)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sfree_bar(t));
+        }
         if (valid < 128) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
@@ -527,7 +659,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (__any_sync(0xffffffffu, need)) {
           const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
           if (j > sg.t0) {
-            // S_t(j) complete implies PV_t(j-1) complete (tensor pipe is in-order), so O is stable
+            // O must be stable: PV_t(j-1) complete (TMEM-P: implied by S_t(j); early-QK: wait for it)
+            if (!prev_pv_done) {
+              mbar_wait(odone_bar(t), (cnt - 2) & 1);
+              tc_fence_after();
+              prev_pv_done = true;
+            }
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               uint32_t ov[32];
@@ -566,6 +703,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if constexpr (kPTmem) {
             tmem_st16(t_s + cc * 16, pk);
           } else {
+            // the P buffer is still being read by PV_t(j-1) until its commit arrives
+            if (!prev_pv_done) {
+              mbar_wait(odone_bar(t), (cnt - 2) & 1);
+              prev_pv_done = true;
+            }
             // P tile [128 rows x 128 keys], K-major SW128: two 64-key boxes, 16-byte chunks XOR row%8
             uint8_t* prow = p_gen + t * kTileBytes + (cc >> 1) * kBoxBytes + row_in_tile * 128;
 #pragma unroll
