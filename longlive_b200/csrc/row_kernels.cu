@@ -54,7 +54,7 @@ __device__ __forceinline__ float absmax8(const uint4& v) {
 
 // kFp8Out: the modulated row is additionally quantised for the FP8 linear that consumes it:
 // per-row scale = amax / 448 (e4m3 max), out8 = round(y / scale); the bf16 output is skipped.
-template <bool kFp8Out>
+template <bool kFp8Out, int NV>
 __global__ void __launch_bounds__(kRowWarps * 32)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                    int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ shift,
@@ -67,10 +67,10 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
   if (row >= rows) return;
   const int nvec = C / 8;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
-  uint4 v[kMaxVec];
+  uint4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       v[i] = xr[vi];
@@ -79,10 +79,28 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
       for (int e = 0; e < 4; ++e) s += bf16_lo(w[e]) + bf16_hi(w[e]);
     }
   }
+  // the per-frame shift / scale (or the affine weight / bias) do not depend on the statistics:
+  // fetch them now so their latency overlaps the two warp reductions
+  const bool affine = ln_w != nullptr;
+  const int64_t mrow = static_cast<int64_t>((row0 + row) / rows_per_frame) * ld_mod;
+  uint4 av[NV], bv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      if (affine) {
+        av[i] = __ldg(reinterpret_cast<const uint4*>(ln_w) + vi);
+        bv[i] = __ldg(reinterpret_cast<const uint4*>(ln_b) + vi);
+      } else {
+        av[i] = __ldg(reinterpret_cast<const uint4*>(scale + mrow) + vi);
+        bv[i] = __ldg(reinterpret_cast<const uint4*>(shift + mrow) + vi);
+      }
+    }
+  }
   const float mean = warp_sum(s) / static_cast<float>(C);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
@@ -94,25 +112,15 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
-  const bool affine = ln_w != nullptr;
-  const int64_t mrow = static_cast<int64_t>((row0 + row) / rows_per_frame) * ld_mod;
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
   float amax = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
-      uint4 a4, b4;
-      if (affine) {
-        a4 = __ldg(reinterpret_cast<const uint4*>(ln_w) + vi);
-        b4 = __ldg(reinterpret_cast<const uint4*>(ln_b) + vi);
-      } else {
-        a4 = __ldg(reinterpret_cast<const uint4*>(scale + mrow) + vi);
-        b4 = __ldg(reinterpret_cast<const uint4*>(shift + mrow) + vi);
-      }
-      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a4);
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b4);
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av[i]);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv[i]);
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -142,7 +150,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
     const float inv = 1.0f / sc;
     uint2* o8 = reinterpret_cast<uint2*>(out8 + static_cast<int64_t>(row) * ld8);
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) o8[vi] = quant8_e4m3(v[i], inv);
     }
@@ -243,6 +251,7 @@ __device__ __forceinline__ int ring_dst_row(const llb_step_params* sp, int row) 
   return -1;
 }
 
+template <int NV>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv,
                            __nv_bfloat16* __restrict__ q_out, int64_t ldq,
@@ -259,12 +268,16 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
   const uint4* qr = reinterpret_cast<const uint4*>(qkv + base);
   const uint4* kr = reinterpret_cast<const uint4*>(qkv + base + C);
   const uint4* vr = reinterpret_cast<const uint4*>(qkv + base + 2 * C);
-  uint4 qv[kMaxVec], kv[kMaxVec];
+  // all of this row's traffic is issued up front: q, k, v and the two norm weights
+  uint4 qv[NV], kv[NV], vv[NV], wqv[NV], wkv[NV];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (lane + i * 32 < nvec) {
       qv[i] = qr[lane + i * 32];
       kv[i] = kr[lane + i * 32];
+      vv[i] = vr[lane + i * 32];
+      wqv[i] = __ldg(reinterpret_cast<const uint4*>(wq) + lane + i * 32);
+      wkv[i] = __ldg(reinterpret_cast<const uint4*>(wk) + lane + i * 32);
     }
   }
   const float q_rstd = rsqrtf(row_sumsq(qv, lane, nvec) / static_cast<float>(C) + eps);
@@ -284,13 +297,12 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
   uint4* ko = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
   uint4* vo = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       // this vector covers channels [8*vi, 8*vi+8) = complex pairs 4*(vi%16) .. +3 of head vi/16
       const int pair0 = (vi & 15) * 4;
-      const uint4 wq4 = __ldg(reinterpret_cast<const uint4*>(wq) + vi);
-      const uint4 wk4 = __ldg(reinterpret_cast<const uint4*>(wk) + vi);
+      const uint4 wq4 = wqv[i], wk4 = wkv[i];
       const uint32_t* qw = reinterpret_cast<const uint32_t*>(&qv[i]);
       const uint32_t* kw = reinterpret_cast<const uint32_t*>(&kv[i]);
       const uint32_t* gq = reinterpret_cast<const uint32_t*>(&wq4);
@@ -313,7 +325,7 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
         qo[vi] = make_uint4(oq[0], oq[1], oq[2], oq[3]);
         if (dst >= 0) {
           ko[vi] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
-          vo[vi] = vr[vi];
+          vo[vi] = vv[i];
         }
       } else {
         // head exchange fused into the store: this 16-byte vector belongs to head vi/16, owned by
@@ -454,7 +466,8 @@ extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ld
   LLB_CHECK_ARG(affine ? (ln_b != nullptr) : (shift && scale && rows_per_frame > 0),
                 "ln_modulate: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  ln_modulate_kernel<false><<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = (C + 255) / 256 <= 6 ? ln_modulate_kernel<false, 6> : ln_modulate_kernel<false, kMaxVec>;
+  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
       rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
@@ -474,7 +487,8 @@ extern "C" int llb_ln_modulate_fp8(const void* x, int64_t ldx, void* out8, int64
   LLB_CHECK_ARG(affine ? (ln_b != nullptr) : (shift && scale && rows_per_frame > 0),
                 "ln_modulate_fp8: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  ln_modulate_kernel<true><<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = (C + 255) / 256 <= 6 ? ln_modulate_kernel<true, 6> : ln_modulate_kernel<true, kMaxVec>;
+  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, nullptr, 0, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
       rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
@@ -532,7 +546,8 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
   LLB_CHECK_ARG(ld_qkv % 8 == 0 && ldq % 8 == 0 && ld_cache % 8 == 0 && grid_h > 0 && grid_w > 0,
                 "rmsnorm_rope_append: bad strides / grid");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  rmsnorm_rope_append_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kern = (C + 255) / 256 <= 6 ? rmsnorm_rope_append_kernel<6> : rmsnorm_rope_append_kernel<kMaxVec>;
+  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(q_out), ldq,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), ld_cache, rows, C,
       static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), eps,
