@@ -9,16 +9,27 @@
 //   (:460), SiLU (:606).  Rounding points mirror the reference (bf16 after the Linear, after the
 //   gate multiply, after the residual add) so the result is bit-comparable to the PyTorch path.
 //
-// Structure (one CTA per SM, 192 threads):
-//   warp 0      TMA producer: A tile [128 x 64] and W tile [BN x 64] per k-block into a
-//               kStages-deep shared-memory ring (SWIZZLE_128B), full/empty mbarriers
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block into
-//               one of two TMEM accumulator stages; tcgen05.commit frees smem slots / signals
-//               the epilogue
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread == row), add bias, activation,
-//               round to bf16, transpose through a small shared-memory staging buffer so that
-//               global stores (and residual/gate loads) are 128-byte coalesced
+// Structure (one CTA per SM, 320 threads):
+//   warp 0      TMA producer: A tile [128 x 64] and W tile per k-block into a kStages-deep
+//               shared-memory ring (SWIZZLE_128B), full/empty mbarriers
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma x4 per k-block into one of two
+//               TMEM accumulator stages; tcgen05.commit frees smem slots / signals the epilogue
+//   warps 2..9  epilogue: two warps per TMEM lane quadrant, each taking every other 32-column
+//               slab: tcgen05.ld (thread == row), bias, activation, round to bf16, transpose
+//               through a swizzled shared-memory staging buffer so that global stores (and
+//               residual / gate loads) are coalesced 64-byte row segments
 // The two TMEM stages let tile i's epilogue overlap tile i+1's main loop.
+//
+// Two tile modes.  The main loop is bound by L2 -> SM bytes, not by the tensor pipe (ncu: ~14.5 TB/s
+// of xbar reads at 60 % tensor-pipe activity with 128 x 192 tiles), so the mode that moves fewer bytes
+// per flop wins whenever the tile count still fills the machine:
+//   single  one CTA computes a 128 x BN tile            (16 KB A + BN*128 B W per k-block)
+//   pair    a cluster of two CTAs on one TPC computes a 256 x BN tile with cta_group::2 MMAs: each
+//           CTA loads its own 128 rows of A and HALF of the W tile (16 KB + BN*64 B per k-block),
+//           the leader CTA issues the MMAs for both, each CTA's TMEM receives its 128 rows and
+//           its own epilogue warps drain them.
+#include <stdlib.h>
+
 #include "llb_common.cuh"
 #include "llb_host.h"
 
@@ -26,22 +37,27 @@ namespace llb {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
-constexpr int kEpiStageBytesPerWarp = 32 * 144;  // 32 rows x (128 B + 16 B pad)
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kEpiStageBytesPerWarp = 32 * 64;  // 32 rows x 32 bf16 columns, 16-byte chunks xor-swizzled
 
-template <int BN>
+template <int BN, bool kPair>
 struct GemmCfg {
   static constexpr int kStageA = kBM * kBK * 2;
-  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kRowsB = kPair ? BN / 2 : BN;  // W rows this CTA loads per k-block
+  static constexpr int kStageB = kRowsB * kBK * 2;
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   // TMEM allocations are powers of two >= 32 columns; two accumulator stages of BN columns each
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kEpiVecBytesPerWarp = 2 * BN * 4;  // per-warp fp32 bias[BN] and w_scale[BN]
-  static constexpr int kSmemBytes =
-      1024 /*align slack*/ + kStages * kStageBytes + 4 * (kEpiStageBytesPerWarp + kEpiVecBytesPerWarp) +
-      256 /*barriers*/;
-  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+  // per epilogue warp: fp32 bias and w_scale for the BN/2 columns it owns
+  static constexpr int kEpiVecBytesPerWarp = 2 * (BN / 2) * 4;
+  static constexpr int kEpiBytes = kEpiWarps * (kEpiStageBytesPerWarp + kEpiVecBytesPerWarp);
+  static constexpr int kFixedBytes = 1024 /*align slack*/ + kEpiBytes + 256 /*barriers*/;
+  static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
+  static_assert(kStages >= 3 && kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+  static_assert(2 * kStages + 5 <= 32, "barrier block is 256 bytes");
 };
 
 struct GemmParams {
@@ -56,7 +72,7 @@ struct GemmParams {
   int gate_row0;
   const __nv_bfloat16* res;
   int64_t ld_res;
-  int num_m_tiles, num_n_tiles;
+  int num_m_tiles, num_n_tiles;  // pair mode: num_m_tiles counts 256-row tiles
   const float* a_scale;  // fp8 path: per-row activation scale [M]
   const float* w_scale;  // fp8 path: per-output-channel weight scale [N]
 };
@@ -74,20 +90,21 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // kFp8: A and W are e4m3 bytes (K-block = 128 elements = the same 128-byte swizzle row), the MMA is
 // kind::f8f6f4 (K = 32 per instruction, twice the bf16 rate) and the epilogue applies
 // a_scale[row] * w_scale[col] before the bias.
-template <int BN, bool kFp8>
+template <int BN, bool kFp8, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kPair>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
+  // SWIZZLE_128B tiles need 1024-byte alignment (the dynamic smem base is the same in both CTAs of a
+  // pair, so every offset below is too - cta_group::2 MMAs and multicast commits rely on that)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t stage_base = smem_base;
   const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
   uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
-  const uint32_t bar_base = epi_base + 4 * (kEpiStageBytesPerWarp + Cfg::kEpiVecBytesPerWarp);
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
   // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -95,11 +112,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(epi_gen + 4 * (kEpiStageBytesPerWarp + Cfg::kEpiVecBytesPerWarp) +
-                                           8 * (2 * kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::kEpiBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int worker = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_workers = kPair ? (gridDim.x >> 1) : gridDim.x;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   constexpr int kKElems = kFp8 ? 128 : kBK;  // elements per k-block (always 128 bytes)
   const int num_kb = (p.K + kKElems - 1) / kKElems;
@@ -113,16 +132,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      // one arrive per epilogue warp; in pair mode the leader's barrier also collects the peer's
+      mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -131,16 +157,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int m_idx = tile % p.num_m_tiles;
         const int n_idx = tile / p.num_m_tiles;
+        const int a_row = kPair ? (m_idx * 2 + static_cast<int>(cta_rank)) * kBM : m_idx * kBM;
+        const int b_row = n_idx * BN + (kPair ? static_cast<int>(cta_rank) * (BN / 2) : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kStageA;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kKElems, m_idx * kBM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kKElems, n_idx * BN);
+          if constexpr (kPair) {
+            // both CTAs' bytes are counted on the leader's barrier, which the leader arms once
+            const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tmap_a, lead_full, kb * kKElems, a_row);
+            tma_load_2d_pair(sb, &tmap_b, lead_full, kb * kKElems, b_row);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kKElems, a_row);
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kKElems, b_row);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -148,104 +184,122 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // Whole warp in the loop (so descriptors stay in uniform registers); one elected lane issues.
-    constexpr uint32_t idesc = kFp8 ? umma_idesc_e4m3(kBM, BN) : umma_idesc_bf16(kBM, BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+    // Pair mode: only the leader CTA issues; its commits are multicast to both CTAs' barriers.
+    if (cta_rank == 0) {
+      constexpr int kMmaM = kPair ? 2 * kBM : kBM;
+      constexpr uint32_t idesc = kFp8 ? umma_idesc_e4m3(kMmaM, BN) : umma_idesc_bf16(kMmaM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kStageA;
-        const uint64_t da = umma_desc_kmajor(sa);
-        const uint64_t db = umma_desc_kmajor(sb);
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = umma_desc_kmajor(sa);
+          const uint64_t db = umma_desc_kmajor(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the
-            // (addr >> 4) field of the descriptor
-            if constexpr (kFp8) umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the
+              // (addr >> 4) field of the descriptor
+              const uint32_t accum = (kb | k) != 0;
+              if constexpr (kPair) {
+                if constexpr (kFp8) umma_ss_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              } else {
+                if constexpr (kFp8) umma_ss_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                else umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+              }
+            }
+            if constexpr (kPair) {
+              umma_commit_pair(empty_bar(stage), 3);
+              if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc), 3);
+            } else {
+              umma_commit(empty_bar(stage));
+              if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+            }
           }
-          umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int h = (warp - 2) >> 2;   // which 32-column slab of every 64 columns it owns
     uint8_t* my_stage = epi_gen + (warp - 2) * kEpiStageBytesPerWarp;
-    float* my_bias =
-        reinterpret_cast<float*>(epi_gen + 4 * kEpiStageBytesPerWarp + (warp - 2) * Cfg::kEpiVecBytesPerWarp);
-    float* my_ws = my_bias + BN;
+    float* my_bias = reinterpret_cast<float*>(epi_gen + kEpiWarps * kEpiStageBytesPerWarp +
+                                              (warp - 2) * Cfg::kEpiVecBytesPerWarp);
+    float* my_ws = my_bias + BN / 2;
+    const uint32_t tempty_lead0 = kPair ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const int epi = p.epilogue;
+    const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES);
+    const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int m_idx = tile % p.num_m_tiles;
       const int n_idx = tile / p.num_m_tiles;
+      const int row_base = (kPair ? (m_idx * 2 + static_cast<int>(cta_rank)) * kBM : m_idx * kBM) + q * 32;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // Stage this tile's bias (and fp8 weight scales) as fp32 in shared memory while the main loop
+      // Stage this warp's bias (and fp8 weight scales) as fp32 in shared memory while the main loop
       // is still running: the per-column values are then broadcast LDS reads instead of global loads
-      // whose latency a single epilogue warp per scheduler cannot hide.
+      // whose latency the epilogue warps cannot hide.
 #pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int cl = lane + i * 32, cg = n_idx * BN + cl;
-        my_bias[cl] = (p.bias != nullptr && cg < p.N) ? __bfloat162float(p.bias[cg]) : 0.f;
-        if constexpr (kFp8) my_ws[cl] = cg < p.N ? __ldg(p.w_scale + cg) : 0.f;
+      for (int i = 0; i < BN / 64; ++i) {
+        const int cg = n_idx * BN + (2 * i + h) * 32 + lane;
+        my_bias[i * 32 + lane] = (p.bias != nullptr && cg < p.N) ? __bfloat162float(p.bias[cg]) : 0.f;
+        if constexpr (kFp8) my_ws[i * 32 + lane] = cg < p.N ? __ldg(p.w_scale + cg) : 0.f;
       }
+      float row_scale = 1.0f;
+      if constexpr (kFp8) row_scale = row_base + lane < p.M ? __ldg(p.a_scale + row_base + lane) : 0.f;
       __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
-        const int col0 = n_idx * BN + c * 64;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t_row + c * 64, v0);
-        tmem_ld32(t_row + c * 64 + 32, v1);
+        const int col0 = n_idx * BN + (2 * c + h) * 32;
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 64, v);
         tmem_wait_ld();
         if (c == BN / 64 - 1) {
-          // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+          // accumulator slabs fully drained into registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_cluster(tempty_lead0 + 8u * acc);
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
-        // phase 1: thread == row.  bias (+activation) -> bf16 -> staging row (128 bytes)
-        uint4* srow = reinterpret_cast<uint4*>(my_stage + lane * 144);
-        float row_scale = 1.0f;
-        if constexpr (kFp8) {
-          const int grow_s = m_idx * kBM + q * 32 + lane;
-          row_scale = grow_s < p.M ? __ldg(p.a_scale + grow_s) : 0.f;
-        }
+        // phase 1: thread == row.  bias (+activation) -> bf16 -> staging row (64 bytes, 4 chunks)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           uint32_t packed[4];
           // 8 bias values (and fp8 scales) for columns col0 + 8g .. +7: broadcast LDS
-          const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c * 64 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c * 64 + g * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c * 32 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c * 32 + g * 8 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float ws[8];
           if constexpr (kFp8) {
-            const float4 w0 = *reinterpret_cast<const float4*>(my_ws + c * 64 + g * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(my_ws + c * 64 + g * 8 + 4);
+            const float4 w0 = *reinterpret_cast<const float4*>(my_ws + c * 32 + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(my_ws + c * 32 + g * 8 + 4);
             ws[0] = w0.x * row_scale; ws[1] = w0.y * row_scale; ws[2] = w0.z * row_scale; ws[3] = w0.w * row_scale;
             ws[4] = w1.x * row_scale; ws[5] = w1.y * row_scale; ws[6] = w1.z * row_scale; ws[7] = w1.w * row_scale;
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = g * 8 + e * 2;  // column inside the 64-wide chunk
-            float a0 = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
-            float a1 = __uint_as_float(j + 1 < 32 ? v0[(j + 1) & 31] : v1[(j + 1) & 31]);
+            const int j = g * 8 + e * 2;  // column inside the 32-wide slab
+            float a0 = __uint_as_float(v[j]);
+            float a1 = __uint_as_float(v[j + 1]);
             if constexpr (kFp8) {
               a0 *= ws[2 * e];
               a1 *= ws[2 * e + 1];
@@ -260,59 +314,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             packed[e] = pack_bf16x2(y0, y1);
           }
-          srow[g] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         __syncwarp();
-        // phase 2: 8 lanes cover one 128-byte row segment -> coalesced global traffic.  Loads of
-        // the residual / gate for four rows are issued together before any arithmetic so their
-        // latency overlaps (one epilogue warp per scheduler has nobody else to hide it).
-        const int seg = lane & 7;
+        // phase 2: 4 lanes cover one 64-byte row segment, 8 rows per pass -> coalesced global traffic.
+        // The residual / gate loads of all four passes are issued together before any arithmetic so
+        // their latencies overlap.
+        const int seg = lane & 3;
         const int gcol = col0 + seg * 8;
         const bool col_ok = gcol < p.N;
-        const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES);
-        const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
+        uint4 yv[4], xv[4], gv[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint4 yv[4], xv[4], gv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (half * 4 + i) * 4 + (lane >> 3);
-            const int grow = m_idx * kBM + q * 32 + r;
-            yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 144 + seg * 16);
-            xv[i] = make_uint4(0, 0, 0, 0);
-            gv[i] = make_uint4(0, 0, 0, 0);
-            if (grow < p.M && col_ok) {
-              if (has_res)
-                xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(grow) * p.ld_res + gcol);
-              if (has_gate)
-                gv[i] = __ldg(reinterpret_cast<const uint4*>(
-                    p.gate + static_cast<int64_t>((grow + p.gate_row0) / p.rows_per_gate) * p.ld_gate + gcol));
-            }
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2);
+          const int grow = row_base + r;
+          yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((seg ^ ((r >> 1) & 3)) << 4));
+          xv[i] = make_uint4(0, 0, 0, 0);
+          gv[i] = make_uint4(0, 0, 0, 0);
+          if (grow < p.M && col_ok) {
+            if (has_res)
+              xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(grow) * p.ld_res + gcol);
+            if (has_gate)
+              gv[i] = __ldg(reinterpret_cast<const uint4*>(
+                  p.gate + static_cast<int64_t>((grow + p.gate_row0) / p.rows_per_gate) * p.ld_gate + gcol));
           }
+        }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (half * 4 + i) * 4 + (lane >> 3);
-            const int grow = m_idx * kBM + q * 32 + r;
-            if (grow < p.M && col_ok) {
-              uint4 y = yv[i];
-              if (has_res) {
-                const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yv[i]);
-                const uint32_t* xx = reinterpret_cast<const uint32_t*>(&xv[i]);
-                const uint32_t* gg = reinterpret_cast<const uint32_t*>(&gv[i]);
-                uint32_t o[4];
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2);
+          const int grow = row_base + r;
+          if (grow < p.M && col_ok) {
+            uint4 y = yv[i];
+            if (has_res) {
+              const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yv[i]);
+              const uint32_t* xx = reinterpret_cast<const uint32_t*>(&xv[i]);
+              const uint32_t* gg = reinterpret_cast<const uint32_t*>(&gv[i]);
+              uint32_t o[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float y0 = bf16_lo(yy[e]), y1 = bf16_hi(yy[e]);
-                  if (has_gate) {
-                    y0 = bf16_round(y0 * bf16_lo(gg[e]));
-                    y1 = bf16_round(y1 * bf16_hi(gg[e]));
-                  }
-                  o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
+              for (int e = 0; e < 4; ++e) {
+                float y0 = bf16_lo(yy[e]), y1 = bf16_hi(yy[e]);
+                if (has_gate) {
+                  y0 = bf16_round(y0 * bf16_lo(gg[e]));
+                  y1 = bf16_round(y1 * bf16_hi(gg[e]));
                 }
-                y = make_uint4(o[0], o[1], o[2], o[3]);
+                o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
               }
-              *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + gcol) = y;
+              y = make_uint4(o[0], o[1], o[2], o[3]);
             }
+            *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + gcol) = y;
           }
         }
         __syncwarp();
@@ -321,30 +371,66 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  __syncthreads();
+  // pair mode: neither CTA may exit (or free its TMEM) while the other can still signal its barriers
+  if constexpr (kPair) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, bool kFp8>
+template <int BN, bool kFp8, bool kPair>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kFp8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
+    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kFp8, kPair>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_kernel<BN, kFp8><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  if constexpr (kPair) {
+    const int clusters = tiles < sms / 2 ? tiles : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LLB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kFp8, kPair>, ta, tb, p));
+  } else {
+    const int grid = tiles < sms ? tiles : sms;
+    gemm_bf16_kernel<BN, kFp8, kPair><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  }
   LLB_LAUNCH_CHECK("gemm_bf16_kernel");
   return LLB_OK;
+}
+
+template <bool kFp8, bool kPair>
+static int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t s) {
+  switch (bn) {
+    case 64:
+      if constexpr (kPair) break;  // a pair tile narrower than 128 columns is never chosen
+      else return launch_gemm<64, kFp8, false>(ta, tb, p, s);
+    case 128: return launch_gemm<128, kFp8, kPair>(ta, tb, p, s);
+    case 192: return launch_gemm<192, kFp8, kPair>(ta, tb, p, s);
+    case 256: return launch_gemm<256, kFp8, kPair>(ta, tb, p, s);
+    default: break;
+  }
+  set_error("gemm: unsupported tile width %d (pair=%d)", bn, static_cast<int>(kPair));
+  return LLB_E_INVALID;
 }
 
 }  // namespace llb
@@ -371,21 +457,37 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(res) & 15) == 0, "gemm: bias/gate/res must be 16-byte aligned");
 
-  // Tile width: minimise (waves over the SMs) x (per-tile MMA time ~ BN), with a penalty for the
-  // narrower tiles whose SS-mode MMAs sit closer to the shared-memory bandwidth limit
-  // (A 4 KB + B BN*32 B per K=16 step of BN/2 cycles: 128 B/clk at BN=128, 107 at 192, 96 at 256).
+  // Tile shape: minimise waves x per-tile time.  The per-tile costs are the measured steady-state time
+  // per k-block (ns, B200, every SM streaming; tools/kernel_bench.py --what tilesweep, see DESIGN.md
+  // section 4.2): the main loop runs at the L2 -> SM transfer rate, so wider tiles and CTA pairs (which
+  // move 1.5-1.7x fewer bytes per flop) are cheaper per flop, but they quantise the tile count coarser.
+  // With e4m3 operands a pair tile is never faster than a single one.
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
   int bn = 64;
+  bool pair = false;
   if (N > 64) {
-    const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-    const int m_tiles = (M + kBM - 1) / kBM;
-    const int cand[3] = {128, 192, 256};
-    const double penalty[3] = {1.15, 1.05, 1.0};
+    static const double kCostBf16[2][3] = {{330, 388, 446}, {275, 325, 420}};  // [pair][bn 128/192/256]
+    static const double kCostFp8[2][3] = {{383, 475, 567}, {375, 475, 600}};
     double best = 1e30;
-    for (int i = 0; i < 3; ++i) {
-      const int tiles = m_tiles * ((N + cand[i] - 1) / cand[i]);
-      const int waves = (tiles + sms - 1) / sms;
-      const double cost = waves * cand[i] * penalty[i];
-      if (cost < best) { best = cost; bn = cand[i]; }
+    for (int pr = 0; pr < 2; ++pr) {
+      const int workers = pr ? sms / 2 : sms;
+      const int m_tiles = pr ? (M + 2 * kBM - 1) / (2 * kBM) : (M + kBM - 1) / kBM;
+      for (int i = 0; i < 3; ++i) {
+        const int cand = 128 + 64 * i;
+        const int tiles = m_tiles * ((N + cand - 1) / cand);
+        const int waves = (tiles + workers - 1) / workers;
+        const double cost = waves * (fp8 ? kCostFp8[pr][i] : kCostBf16[pr][i]);
+        if (cost < best) { best = cost; bn = cand; pair = pr != 0; }
+      }
+    }
+  }
+  // debugging / benchmarking override: LLB_GEMM_TILE="<pair 0|1>,<bn>"
+  const char* force = getenv("LLB_GEMM_TILE");
+  if (force != nullptr && N > 64) {
+    int fp = 0, fb = 0;
+    if (sscanf(force, "%d,%d", &fp, &fb) == 2 && (fb == 128 || fb == 192 || fb == 256)) {
+      pair = fp != 0;
+      bn = fb;
     }
   }
 
@@ -397,35 +499,27 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.gate_row0 = gate_row0;
   p.res = static_cast<const __nv_bfloat16*>(res); p.ld_res = ld_res;
-  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_m_tiles = pair ? (M + 2 * kBM - 1) / (2 * kBM) : (M + kBM - 1) / kBM;
   p.num_n_tiles = (N + bn - 1) / bn;
   p.a_scale = a_scale;
   p.w_scale = w_scale;
 
   CUtensorMap ta, tb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int b_box_rows = pair ? bn / 2 : bn;  // each CTA of a pair loads half of the W tile
+  int rc;
   if (fp8) {
-    int rc = make_tmap_2d_u8(&ta, A, M, K, lda, kBM, 128);
+    rc = make_tmap_2d_u8(&ta, A, M, K, lda, kBM, 128);
     if (rc) return rc;
-    rc = make_tmap_2d_u8(&tb, W, N, K, ldw, bn, 128);
+    rc = make_tmap_2d_u8(&tb, W, N, K, ldw, b_box_rows, 128);
     if (rc) return rc;
-    switch (bn) {
-      case 64: return launch_gemm<64, true>(ta, tb, p, s);
-      case 128: return launch_gemm<128, true>(ta, tb, p, s);
-      case 192: return launch_gemm<192, true>(ta, tb, p, s);
-      default: return launch_gemm<256, true>(ta, tb, p, s);
-    }
+    return pair ? dispatch_bn<true, true>(bn, ta, tb, p, s) : dispatch_bn<true, false>(bn, ta, tb, p, s);
   }
-  int rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBM, kBK);
+  rc = make_tmap_2d_bf16(&ta, A, M, K, lda, kBM, kBK);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, bn, kBK);
+  rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, b_box_rows, kBK);
   if (rc) return rc;
-  switch (bn) {
-    case 64: return launch_gemm<64, false>(ta, tb, p, s);
-    case 128: return launch_gemm<128, false>(ta, tb, p, s);
-    case 192: return launch_gemm<192, false>(ta, tb, p, s);
-    default: return launch_gemm<256, false>(ta, tb, p, s);
-  }
+  return pair ? dispatch_bn<false, true>(bn, ta, tb, p, s) : dispatch_bn<false, false>(bn, ta, tb, p, s);
 }
 
 extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,

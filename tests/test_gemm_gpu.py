@@ -98,3 +98,53 @@ def test_gemm_epilogues(epi):
     assert err < 5e-3, f"{epi}: rel-L2 {err}"
 
 
+
+
+# Every tile mode the heuristic can pick (single CTA or CTA pair x tile width), forced through the
+# library's LLB_GEMM_TILE override, on ragged shapes: M not a multiple of 256 (the second CTA of the
+# last pair is partly / entirely out of bounds), N not a multiple of the tile width, K tail.
+TILE_MODES = [(0, 128), (0, 192), (0, 256), (1, 128), (1, 192), (1, 256)]
+
+
+@pytest.fixture
+def force_tile(monkeypatch):
+    def _set(pair, bn):
+        monkeypatch.setenv("LLB_GEMM_TILE", f"{pair},{bn}")
+    yield _set
+    monkeypatch.delenv("LLB_GEMM_TILE", raising=False)
+
+
+@pytest.mark.parametrize("pair,bn", TILE_MODES)
+@pytest.mark.parametrize("M,N,K", [(4680, 1536, 1536), (1560, 4608, 512), (72, 136, 200), (385, 8960, 320),
+                                   (129, 200, 64), (300, 1536, 8960)])
+def test_gemm_tile_modes(force_tile, pair, bn, M, N, K):
+    ops = _ops()
+    force_tile(pair, bn)
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = bf(torch.randn(N, generator=g)).to(DEV)
+    x = bf(torch.randn(M, N, generator=g)).to(DEV)
+    guard = torch.full((M + 4, N), 7.0, dtype=torch.bfloat16, device=DEV)  # rows past M must stay untouched
+    out = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_RES, res=x, out=guard[:M])
+    ref = x.float() + bf(a.float() @ w.float().t() + b.float()).float()
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    assert err < 5e-3, f"pair={pair} bn={bn}: rel-L2 {err}"
+    assert (guard[M:] == 7.0).all()
+
+
+@pytest.mark.parametrize("pair,bn", TILE_MODES)
+def test_gemm_tile_modes_bitwise_equal(force_tile, pair, bn):
+    """All tile modes accumulate each output in the same k order, so they agree bit for bit."""
+    ops = _ops()
+    M, N, K = 1000, 1536, 1536
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    b = bf(torch.randn(N, generator=g)).to(DEV)
+    force_tile(0, 128)
+    base = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_GELU)
+    force_tile(pair, bn)
+    out = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_GELU)
+    assert torch.equal(out, base)

@@ -31,6 +31,29 @@ def timeit(fn, warmup=3, iters=10):
     return st.elapsed_time(en) / iters
 
 
+def sustained(fn, seconds=0.4):
+    """Run fn back to back for `seconds`, sampling the SM clock from another thread: returns
+    (ms per call, median SM MHz while running).  Power-capped kernels must be compared at the clock
+    they actually ran at."""
+    import threading
+    import pynvml
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(0)
+    ms1 = timeit(fn, warmup=2, iters=5)
+    iters = max(10, int(seconds * 1e3 / ms1))
+    clocks, stop = [], threading.Event()
+
+    def sample():
+        while not stop.is_set():
+            clocks.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            stop.wait(0.02)
+    th = threading.Thread(target=sample); th.start()
+    ms = timeit(fn, warmup=iters // 4, iters=iters)
+    stop.set(); th.join()
+    clocks = sorted(clocks[len(clocks) // 3:]) or [0]
+    return ms, clocks[len(clocks) // 2]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--what", default="gemm,attn,row")
@@ -72,6 +95,44 @@ def main():
             ms = timeit(lambda: torch.addmm(b, a, w.t(), out=out), iters=args.iters)
             emit({"kernel": "cublas_addmm", "shape": [M, N, K], "name": name, "ms": ms,
                   "tflops": fl / ms / 1e9})
+    if "tilesweep" in args.what:
+        # every tile mode on the four block GEMM shapes with the epilogue the model uses there
+        for (M, N, K, name, epi) in [(4680, 4608, 1536, "qkv", "bias"), (4680, 1536, 1536, "o", "gate_res"),
+                                     (4680, 8960, 1536, "ffn1", "gelu"), (4680, 1536, 8960, "ffn2", "gate_res")]:
+            a = torch.randn(M, K, device=DEV, dtype=bf)
+            w = torch.randn(N, K, device=DEV, dtype=bf) / math.sqrt(K)
+            b = torch.randn(N, device=DEV, dtype=bf)
+            x = torch.randn(M, N, device=DEV, dtype=bf)
+            gate = torch.randn(3, N, device=DEV, dtype=bf)
+            out = torch.empty(M, N, device=DEV, dtype=bf)
+            a8, sa = ops.quant_rows_fp8(a)
+            w8, sw = ops.quantize_weight_e4m3(w)
+            fl = 2.0 * M * N * K
+            kw = {"bias": dict(), "gelu": dict(epilogue=ops.EPI_BIAS_GELU),
+                  "gate_res": dict(epilogue=ops.EPI_BIAS_GATE_RES, gate=gate, rows_per_gate=M // 3, res=x)}[epi]
+            for mode in ["auto", "0,128", "0,192", "0,256", "1,128", "1,192", "1,256"]:
+                if mode == "auto":
+                    os.environ.pop("LLB_GEMM_TILE", None)
+                else:
+                    os.environ["LLB_GEMM_TILE"] = mode
+                for kind in ("bf16", "fp8"):
+                    try:
+                        if kind == "bf16":
+                            ms, mhz = sustained(lambda: ops.gemm(a, w, b, out=out, **kw))
+                        else:
+                            ms, mhz = sustained(lambda: ops.gemm_fp8(a8, sa, w8, sw, b, out=out, **kw))
+                        # tensor-pipe share: nominal 8192 dense bf16 flop/clk/SM (x2 for fp8) at the sampled clock
+                        peak = 148 * 8192 * mhz * 1e6 * (2 if kind == "fp8" else 1) / 1e12
+                        emit({"kernel": "llb_gemm_" + kind, "name": name, "epi": epi, "tile": mode,
+                              "ms": round(ms, 5), "tflops": round(fl / ms / 1e9, 1), "sm_mhz": mhz,
+                              "pipe_frac": round(fl / ms / 1e9 / peak, 3) if mhz else None})
+                    except Exception as e:
+                        emit({"kernel": "llb_gemm_" + kind, "name": name, "tile": mode, "error": str(e)[:200]})
+            os.environ.pop("LLB_GEMM_TILE", None)
+            ms, mhz = sustained(lambda: torch.addmm(b, a, w.t(), out=out))
+            emit({"kernel": "cublas_addmm", "name": name, "epi": "bias", "tile": "cublas", "ms": round(ms, 5),
+                  "tflops": round(fl / ms / 1e9, 1), "sm_mhz": mhz,
+                  "pipe_frac": round(fl / ms / 1e9 / (148 * 8192 * mhz * 1e6 / 1e12), 3) if mhz else None})
     if "attn" in args.what:
         H = 12
         for (Lq, Lk) in [(4680, 4680), (4680, 9360), (4680, 18720), (18720, 18720), (4680, 512)]:
