@@ -290,6 +290,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // programmatic dependent launch (see llb_common.cuh): the setup above may overlap the previous
+  // kernel's tail; the kernel after this one may start its own setup as soon as our CTAs drain
+  griddep_wait();
+  griddep_launch_dependents();
 
   // work decomposition: identical in every role, evaluated inside each role branch so that only
   // the state a role needs stays live under its register budget
@@ -850,12 +854,24 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
+  cudaLaunchAttribute attr[2];
+  unsigned n_attr = 0;
   static const bool coop = getenv("LLB_ATTN_COOP") == nullptr || atoi(getenv("LLB_ATTN_COOP")) != 0;
-  cfg.numAttrs = coop ? 1 : 0;
+  if (coop) {
+    attr[n_attr].id = cudaLaunchAttributeCooperative;
+    attr[n_attr].val.cooperative = 1;
+    ++n_attr;
+  }
+  // LLB_ATTN_PDL=1 also launches the attention kernel itself programmatically (off by default: it is
+  // the dependents of this long kernel, not the kernel, that gain from the overlap)
+  static const bool pdl = getenv("LLB_ATTN_PDL") != nullptr && atoi(getenv("LLB_ATTN_PDL")) != 0;
+  if (pdl && pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
   LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;

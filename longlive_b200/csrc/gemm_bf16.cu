@@ -151,6 +151,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous
+  // kernel's tail when launched programmatically; from here on its output is complete and visible.
+  griddep_wait();
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -394,25 +398,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  if constexpr (kPair) {
-    const int clusters = tiles < sms / 2 ? tiles : sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LLB_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kFp8, kPair>, ta, tb, p));
-  } else {
-    const int grid = tiles < sms ? tiles : sms;
-    gemm_bf16_kernel<BN, kFp8, kPair><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  }
+  const int workers = kPair ? sms / 2 : sms;
+  const int grid = (tiles < workers ? tiles : workers) * (kPair ? 2 : 1);
+  LLB_CUDA(launch_ex(gemm_bf16_kernel<BN, kFp8, kPair>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
+                     kPair ? 2 : 1, true, ta, tb, p));
   LLB_LAUNCH_CHECK("gemm_bf16_kernel");
   return LLB_OK;
 }

@@ -102,6 +102,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched with the programmatic-serialization attribute
+// may start (block scheduling, its own prologue) while the previous kernel on the stream is still
+// draining; griddep_wait() then blocks until that previous grid has fully completed and its writes
+// are visible, so everything after it sees ordinary stream order.  Both are no-ops for a kernel
+// launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -2,6 +2,8 @@
 // integer KV-ring planner (the product implementation of the reference's cache index math).
 #include "llb_host.h"
 
+#include <stdlib.h>
+
 #include <stdarg.h>
 #include <string.h>
 
@@ -89,6 +91,14 @@ int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
     return LLB_E_CUDA;
   }
   return LLB_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LLB_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int device_sm_count() {

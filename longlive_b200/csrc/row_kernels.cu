@@ -62,6 +62,8 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
                    int row0, const __nv_bfloat16* __restrict__ ln_w,
                    const __nv_bfloat16* __restrict__ ln_b, float eps, uint8_t* __restrict__ out8,
                    int64_t ld8, float* __restrict__ out_scale) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's output is complete past here
+  griddep_launch_dependents();
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -162,6 +164,8 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
 __global__ void __launch_bounds__(kRowWarps * 32)
 quant_rows_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* __restrict__ out8,
                       int64_t ld8, float* __restrict__ out_scale, int rows, int C) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's output is complete past here
+  griddep_launch_dependents();
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -200,6 +204,8 @@ __device__ __forceinline__ float row_sumsq(const uint4 (&v)[NV], int lane, int n
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ wgt, float eps) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's output is complete past here
+  griddep_launch_dependents();
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -260,6 +266,8 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
                            const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
                            float eps, const float2* __restrict__ rope_cs, int grid_h, int grid_w,
                            const llb_step_params* __restrict__ sp, const llb_qkv_shard sh) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's output is complete past here
+  griddep_launch_dependents();
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -467,11 +475,11 @@ extern "C" int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ld
                 "ln_modulate: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   auto kern = (C + 255) / 256 <= 6 ? ln_modulate_kernel<false, 6> : ln_modulate_kernel<false, kMaxVec>;
-  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  LLB_CUDA(launch_ex(kern, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
       rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
-      static_cast<const __nv_bfloat16*>(ln_b), eps, nullptr, 0, nullptr);
+      static_cast<const __nv_bfloat16*>(ln_b), eps, nullptr, 0, nullptr));
   LLB_LAUNCH_CHECK("ln_modulate_kernel");
   return LLB_OK;
 }
@@ -488,11 +496,11 @@ extern "C" int llb_ln_modulate_fp8(const void* x, int64_t ldx, void* out8, int64
                 "ln_modulate_fp8: need (ln_w, ln_b) or (shift, scale, rows_per_frame)");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   auto kern = (C + 255) / 256 <= 6 ? ln_modulate_kernel<true, 6> : ln_modulate_kernel<true, kMaxVec>;
-  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  LLB_CUDA(launch_ex(kern, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(x), ldx, nullptr, 0, rows, C,
       static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), ld_mod,
       rows_per_frame > 0 ? rows_per_frame : 1, row0, static_cast<const __nv_bfloat16*>(ln_w),
-      static_cast<const __nv_bfloat16*>(ln_b), eps, static_cast<uint8_t*>(out8), ld8, out_scale);
+      static_cast<const __nv_bfloat16*>(ln_b), eps, static_cast<uint8_t*>(out8), ld8, out_scale));
   LLB_LAUNCH_CHECK("ln_modulate_kernel<fp8>");
   return LLB_OK;
 }
@@ -502,8 +510,8 @@ extern "C" int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_
   LLB_CHECK_ARG(x && out8 && out_scale && rows > 0 && C > 0 && C % 8 == 0, "quant_rows_fp8: bad arguments");
   LLB_CHECK_ARG(ldx % 8 == 0 && ld8 % 16 == 0, "quant_rows_fp8: leading dims");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  quant_rows_fp8_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out8), ld8, out_scale, rows, C);
+  LLB_CUDA(launch_ex(quant_rows_fp8_kernel, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out8), ld8, out_scale, rows, C));
   LLB_LAUNCH_CHECK("quant_rows_fp8_kernel");
   return LLB_OK;
 }
@@ -514,9 +522,9 @@ extern "C" int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, i
   LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "rmsnorm: C=%d unsupported", C);
   LLB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0, "rmsnorm: leading dims % 8");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
-  rmsnorm_kernel<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  LLB_CUDA(launch_ex(rmsnorm_kernel, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,
-      static_cast<const __nv_bfloat16*>(w), eps);
+      static_cast<const __nv_bfloat16*>(w), eps));
   LLB_LAUNCH_CHECK("rmsnorm_kernel");
   return LLB_OK;
 }
@@ -547,11 +555,11 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
                 "rmsnorm_rope_append: bad strides / grid");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   auto kern = (C + 255) / 256 <= 6 ? rmsnorm_rope_append_kernel<6> : rmsnorm_rope_append_kernel<kMaxVec>;
-  kern<<<grid, kRowWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  LLB_CUDA(launch_ex(kern, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(q_out), ldq,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), ld_cache, rows, C,
       static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), eps,
-      static_cast<const float2*>(rope_cs), grid_h, grid_w, p_dev, sh);
+      static_cast<const float2*>(rope_cs), grid_h, grid_w, p_dev, sh));
   LLB_LAUNCH_CHECK("rmsnorm_rope_append_kernel");
   return LLB_OK;
 }
