@@ -55,7 +55,7 @@ int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 
 int device_sm_count();
 
-// Programmatic dependent launch is on unless LLB_PDL=0 (read once).
+// Programmatic dependent launch is opt-in: LLB_PDL=1 (read once).
 bool pdl_enabled();
 
 // Launch through cudaLaunchKernelEx with the optional attributes this library uses: a cluster width and
