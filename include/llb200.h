@@ -143,6 +143,7 @@ int llb_peer_barrier(void* const* flags_peers_dev, int rank, int n_ranks, void* 
 #define LLB_EPI_BIAS_SILU 2     /* silu(y)                 (time_embedding, :606)            */
 #define LLB_EPI_BIAS_GATE_RES 3 /* res + y * gate[row / rows_per_gate]   (:456, :467-468)    */
 #define LLB_EPI_BIAS_RES 4      /* res + y                 (cross-attn residual, :460)       */
+#define LLB_EPI_BIAS_F32 5      /* y written as float32 (out is float*, ldo in floats): attention logits of the VAE decoder */
 
 int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                   int M, int N, int K, int epilogue, const void* bias, const void* gate,
@@ -226,6 +227,50 @@ int llb_sinusoidal(const float* t, void* out, int n, int dim, void* stream);
 int llb_modulation_table(const void* modulation, const void* e0, void* out, int n_layers,
                          int n_frames, int width, void* stream);
 int llb_silu(const void* x, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Streaming VAE decoder kernels (reference wan/modules/vae.py, called from
+ * WanVAEWrapper.decode_to_pixel, utils/wan_wrapper.py:96-117).  Activations are channels-last bf16
+ * [frames, H, W, Cp], Cp = channel count padded to a multiple of 64 (pad channels stay exactly 0).
+ * A tensor that feeds a causal convolution is a RING of frames: the new frames of a call sit at ring
+ * positions t0 .. t0+T-1 (mod frames) and the two positions before them hold the previous call's last
+ * two frames - the reference's per-conv feat_cache (vae.py:202-220) without a copy.  A zeroed ring is
+ * the zero padding at the start of a stream.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct llb_conv3d_desc {
+  const void* in;       /* [in_frames, H, W, Cin] bf16 ring */
+  int in_frames, in_t0; /* ring length; ring index of the first new frame */
+  int H, W, Cin, Cout;  /* Cin, Cout: padded, multiples of 64 */
+  const void* weight;   /* [Cout, kt*kh*kw*Cin] bf16: tap-major, k = ((dt*kh + dh)*kw + dw)*Cin + c */
+  const void* bias;     /* [Cout] bf16 or NULL */
+  int kt, kh, kw;       /* 3x3x3, 3x1x1, 1x3x3 or 1x1x1; causal in t, zero "same" padding in h / w */
+  void* out;            /* [out_frames, H, W, Cout] bf16; frame t goes to ring index (out_t0 + t*out_t_step) % out_frames */
+  int out_frames, out_t0, out_t_step;
+  const void* res;      /* optional [res_frames, H, W, Cout]: out = bf16(res + bf16(conv + bias)); may alias out */
+  int res_frames, res_t0;
+  int T;                /* frames to produce */
+} llb_conv3d_desc;
+/* CausalConv3d.forward (vae.py:28-36) / the per-frame nn.Conv2d of Resample (vae.py:76-83) as an implicit
+ * GEMM on tcgen05: TMA loads one shifted [8 x 16 pixel x 64 channel] box per (tap, channel chunk). */
+int llb_conv3d(const llb_conv3d_desc* d, void* stream);
+/* RMS_norm.forward (vae.py:51-54) over the C real channels of every pixel, optionally followed by SiLU
+ * (the RMS_norm -> SiLU pairs of ResidualBlock / head, vae.py:193-199, 415-417); gamma [Cp] bf16, 0 in the pad. */
+int llb_vae_norm(const void* in, int in_frames, int in_t0, void* out, int out_frames, int out_t0, int T,
+                 int64_t pixels, int Cp, int C, const void* gamma, int silu, void* stream);
+/* nn.Upsample(scale_factor=(2,2), mode="nearest") per frame (vae.py:57-63): [T,H,W,Cp] -> [T,2H,2W,Cp] */
+int llb_vae_upsample2x(const void* in, void* out, int T, int H, int W, int Cp, void* stream);
+/* out[c][r] = in[r][c] (bf16) */
+int llb_transpose_bf16(const void* in, int64_t ld_in, void* out, int64_t ld_out, int rows, int cols, void* stream);
+/* P = softmax(logits * scale) over the first cols_valid columns of each fp32 row, bf16 out, columns
+ * [cols_valid, cols_pad) zeroed: the softmax of AttentionBlock's single-head SDPA (vae.py:251-256). */
+int llb_softmax_rows(const float* logits, int64_t ld, void* out, int64_t ldo, int rows, int cols_valid,
+                     int cols_pad, float scale, void* stream);
+/* cached_decode prologue (vae.py:573-579): z [zc, T, h*w] bf16 -> bf16(bf16(z / inv_std) + mean) -> conv2
+ * (1x1x1, w [zc, zc], b [zc]) -> channels-last ring [out_frames, h*w, Cp] */
+int llb_vae_latent_in(const void* z, const void* mean, const void* inv_std, const void* w, const void* b,
+                      void* out, int out_frames, int out_t0, int T, int zc, int64_t hw, int Cp, void* stream);
+/* decode_to_pixel epilogue (utils/wan_wrapper.py:112): [T, h*w, Cp] bf16 -> float [T, 3, h*w] clamped to [-1, 1] */
+int llb_vae_pixel_out(const void* in, float* out, int T, int64_t hw, int Cp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 LLB_MAX_SEGS = 4
 
 # epilogues (include/llb200.h)
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES = range(5)
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_F32 = range(6)
 
 
 class KvState(C.Structure):
@@ -93,6 +93,18 @@ class OutShard(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rows_per_rank", C.c_int32), ("head_col0", C.c_int32),
                 ("reserved", C.c_int32), ("ld_out", C.c_int64), ("out_peers", C.c_void_p * LLB_MAX_RANKS)]
 
+class Conv3dDesc(C.Structure):
+    """llb_conv3d_desc (include/llb200.h): one causal convolution over channels-last frame rings."""
+
+    _fields_ = [("inp", C.c_void_p), ("in_frames", C.c_int), ("in_t0", C.c_int),
+                ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int),
+                ("out", C.c_void_p), ("out_frames", C.c_int), ("out_t0", C.c_int), ("out_t_step", C.c_int),
+                ("res", C.c_void_p), ("res_frames", C.c_int), ("res_t0", C.c_int),
+                ("T", C.c_int)]
+
+
 _PROTOS = {
     # name: (restype, argtypes)
     "llb_version": (C.c_int, []),
@@ -151,6 +163,20 @@ _PROTOS = {
     "llb_modulation_table": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "llb_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "llb_conv3d": (C.c_int, [C.POINTER(Conv3dDesc), C.c_void_p]),
+    "llb_vae_norm": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+         C.c_void_p, C.c_int, C.c_void_p]),
+    "llb_vae_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "llb_transpose_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "llb_softmax_rows": (
+        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "llb_vae_latent_in": (
+        C.c_int,
+        [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.c_int64, C.c_int, C.c_void_p]),
+    "llb_vae_pixel_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

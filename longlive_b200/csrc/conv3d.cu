@@ -1,0 +1,335 @@
+// llb_conv3d - causal 3-D convolution on channels-last activations as an implicit GEMM on tcgen05.
+//
+//   out[t, h, w, :] = bias + sum over taps (dt, dh, dw) of  W[:, tap, :] . in[t + dt - (kt-1), h + dh - kh/2, w + dw - kw/2, :]
+//
+// This is the convolution of the reference's streaming VAE decoder (wan/modules/vae.py:17-36 CausalConv3d,
+// and the per-frame nn.Conv2d of Resample, :66-100, as the kt = 1 case): zero padding in h / w, causal in t,
+// where the frames before the current call are the two-frame history the callers keep (feat_cache, :202-220).
+// Here the history is not a separate tensor: the input is a ring of frames, the new frames are written at
+// ring positions in_t0 .. in_t0 + T - 1 by the producing kernel and the taps at t - 1, t - 2 simply read the
+// positions before them (zero-initialised ring == zero padding at the start of a stream).
+//
+// Structure: the persistent tcgen05 GEMM of gemm_bf16.cu with a different A operand.  One CTA tile is an
+// 8 x 16 pixel patch of one frame (M = 128 rows) times BN output channels; the K loop runs over
+// (tap, 64-channel chunk); for each k-block the TMA producer loads the patch shifted by the tap with ONE 4-D
+// box (c, w, h, frame) - coordinates outside the image, negative ones included, are zero-filled by the TMA
+// unit, which is the spatial zero padding - and the matching [BN x 64] slice of the tap-major weight matrix.
+// The MMA warp and the 8 epilogue warps are the GEMM's; the epilogue maps tile rows back to pixels and adds
+// the residual (x + h of ResidualBlock, vae.py:220) after rounding conv + bias to bf16, as the reference does.
+#include <stdlib.h>
+
+#include "llb_common.cuh"
+#include "llb_host.h"
+
+namespace llb {
+
+constexpr int kConvTH = 8, kConvTW = 16;  // pixel patch = 128 GEMM rows
+constexpr int kConvBK = 64;
+constexpr int kConvEpiWarps = 8;
+constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
+constexpr int kConvEpiStageBytesPerWarp = 32 * 64;
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kStageA = 128 * kConvBK * 2;
+  static constexpr int kStageB = BN * kConvBK * 2;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kEpiVecBytesPerWarp = (BN / 2) * 4;
+  static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp);
+  static constexpr int kFixedBytes = 1024 + kEpiBytes + 256;
+  static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
+  static_assert(kStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
+};
+
+struct ConvParams {
+  int H, W, Cin, Cout, T;
+  int kt, kh, kw;
+  int in_frames, in_t0;
+  __nv_bfloat16* out;
+  int out_frames, out_t0, out_t_step;
+  const __nv_bfloat16* res;
+  int res_frames, res_t0;
+  const __nv_bfloat16* bias;
+  int tiles_h, tiles_w, num_n_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+              const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stage_base = smem_base;
+  const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
+  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::kEpiBytes + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_frame = p.tiles_h * p.tiles_w;
+  const int num_m_tiles = p.T * tiles_per_frame;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+  const int cchunks = p.Cin / kConvBK;
+  const int taps = p.kt * p.kh * p.kw;
+  const int num_kb = taps * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_in);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), kConvEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_idx = tile % num_m_tiles;
+        const int n_idx = tile / num_m_tiles;
+        const int t = m_idx / tiles_per_frame;
+        const int rem = m_idx - t * tiles_per_frame;
+        const int h0 = (rem / p.tiles_w) * kConvTH;
+        const int w0 = (rem % p.tiles_w) * kConvTW;
+        int kb = 0;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          // causal: tap dt reads frame t + dt - (kt - 1) of the stream = ring slot before the new frames
+          int tin = (p.in_t0 + t + dt - (p.kt - 1)) % p.in_frames;
+          if (tin < 0) tin += p.in_frames;
+          for (int dh = 0; dh < p.kh; ++dh) {
+            for (int dw = 0; dw < p.kw; ++dw) {
+              const int tap = (dt * p.kh + dh) * p.kw + dw;
+              for (int cc = 0; cc < cchunks; ++cc, ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+                const uint32_t sb = sa + Cfg::kStageA;
+                mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                tma_load_4d(sa, &tmap_in, full_bar(stage), cc * kConvBK, w0 + dw - p.kw / 2,
+                            h0 + dh - p.kh / 2, tin);
+                tma_load_2d(sb, &tmap_w, full_bar(stage), tap * p.Cin + cc * kConvBK, n_idx * BN);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kStageA;
+        const uint64_t da = umma_desc_kmajor(sa);
+        const uint64_t db = umma_desc_kmajor(sb);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kConvBK / 16; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    uint8_t* my_stage = epi_gen + (warp - 2) * kConvEpiStageBytesPerWarp;
+    float* my_bias = reinterpret_cast<float*>(epi_gen + kConvEpiWarps * kConvEpiStageBytesPerWarp +
+                                              (warp - 2) * Cfg::kEpiVecBytesPerWarp);
+    const bool has_res = p.res != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_idx = tile % num_m_tiles;
+      const int n_idx = tile / num_m_tiles;
+      const int t = m_idx / tiles_per_frame;
+      const int rem = m_idx - t * tiles_per_frame;
+      const int h0 = (rem / p.tiles_w) * kConvTH;
+      const int w0 = (rem % p.tiles_w) * kConvTW;
+      const int t_out = (p.out_t0 + t * p.out_t_step) % p.out_frames;
+      const int t_res = has_res ? (p.res_t0 + t) % p.res_frames : 0;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+#pragma unroll
+      for (int i = 0; i < BN / 64; ++i) {
+        const int cg = n_idx * BN + (2 * i + h) * 32 + lane;
+        my_bias[i * 32 + lane] = (p.bias != nullptr && cg < p.Cout) ? __bfloat162float(p.bias[cg]) : 0.f;
+      }
+      __syncwarp();
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = n_idx * BN + (2 * c + h) * 32;
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 64, v);
+        tmem_wait_ld();
+        if (c == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t packed[4];
+          const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c * 32 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c * 32 + g * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = g * 8 + e * 2;
+            packed[e] = pack_bf16x2(__uint_as_float(v[j]) + bb[2 * e], __uint_as_float(v[j + 1]) + bb[2 * e + 1]);
+          }
+          *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncwarp();
+        const int seg = lane & 3;
+        const int gcol = col0 + seg * 8;
+        const bool col_ok = gcol < p.Cout;
+        uint4 yv[4], xv[4];
+        int64_t off[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2);
+          const int row = q * 32 + r;                     // row of the 8 x 16 patch: h-major
+          const int ph = h0 + (row >> 4), pw = w0 + (row & 15);
+          ok[i] = col_ok && ph < p.H && pw < p.W;
+          off[i] = (static_cast<int64_t>(ph) * p.W + pw) * p.Cout + gcol;
+          yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((seg ^ ((r >> 1) & 3)) << 4));
+          xv[i] = make_uint4(0, 0, 0, 0);
+          if (ok[i] && has_res)
+            xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(t_res) * p.H * p.W * p.Cout + off[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!ok[i]) continue;
+          uint4 y = yv[i];
+          if (has_res) {
+            const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yv[i]);
+            const uint32_t* xx = reinterpret_cast<const uint32_t*>(&xv[i]);
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = pack_bf16x2(bf16_lo(xx[e]) + bf16_lo(yy[e]), bf16_hi(xx[e]) + bf16_hi(yy[e]));
+            y = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(t_out) * p.H * p.W * p.Cout + off[i]) = y;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int sms = device_sm_count();
+  LLB_CHECK_ARG(sms > 0, "no CUDA device");
+  const int tiles = p.T * p.tiles_h * p.tiles_w * p.num_n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  conv3d_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
+  LLB_LAUNCH_CHECK("conv3d_kernel");
+  return LLB_OK;
+}
+
+}  // namespace llb
+
+extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
+  using namespace llb;
+  LLB_CHECK_ARG(d && d->in && d->weight && d->out, "conv3d: null tensor");
+  LLB_CHECK_ARG(d->H > 0 && d->W > 0 && d->T > 0 && d->in_frames > 0 && d->out_frames > 0, "conv3d: bad shape");
+  LLB_CHECK_ARG(d->Cin > 0 && d->Cin % 64 == 0 && d->Cout > 0 && d->Cout % 64 == 0,
+                "conv3d: channel counts must be padded to multiples of 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
+  LLB_CHECK_ARG((d->kt == 1 || d->kt == 3) && (d->kh == 1 || d->kh == 3) && d->kw == d->kh,
+                "conv3d: kernel %dx%dx%d unsupported", d->kt, d->kh, d->kw);
+  LLB_CHECK_ARG(d->in_frames >= d->T + d->kt - 1, "conv3d: input ring of %d frames too short for T=%d, kt=%d",
+                d->in_frames, d->T, d->kt);
+  LLB_CHECK_ARG(d->out_t_step >= 1 && d->out_frames >= (d->T - 1) * d->out_t_step + 1, "conv3d: output ring too short");
+  LLB_CHECK_ARG(d->res == nullptr || d->res_frames >= d->T, "conv3d: residual ring too short");
+  LLB_CHECK_ARG(d->in != d->out, "conv3d: in-place convolution is not supported");
+
+  const int bn = d->Cout % 192 == 0 ? 192 : (d->Cout % 128 == 0 ? 128 : 64);
+  ConvParams p;
+  p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.T = d->T;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
+  p.in_frames = d->in_frames; p.in_t0 = d->in_t0;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_frames = d->out_frames; p.out_t0 = d->out_t0; p.out_t_step = d->out_t_step;
+  p.res = static_cast<const __nv_bfloat16*>(d->res);
+  p.res_frames = d->res_frames > 0 ? d->res_frames : 1; p.res_t0 = d->res_t0;
+  p.bias = static_cast<const __nv_bfloat16*>(d->bias);
+  p.tiles_h = (d->H + kConvTH - 1) / kConvTH;
+  p.tiles_w = (d->W + kConvTW - 1) / kConvTW;
+  p.num_n_tiles = d->Cout / bn;
+
+  CUtensorMap ti, tw;
+  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->Cin, kConvTH, kConvTW, kConvBK);
+  if (rc) return rc;
+  const int64_t kdim = static_cast<int64_t>(d->kt) * d->kh * d->kw * d->Cin;
+  rc = make_tmap_2d_bf16(&tw, d->weight, d->Cout, kdim, kdim, bn, kConvBK);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 192: return launch_conv<192>(ti, tw, p, s);
+    case 128: return launch_conv<128>(ti, tw, p, s);
+    default: return launch_conv<64>(ti, tw, p, s);
+  }
+}

@@ -284,6 +284,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive(tempty_bar(acc));
           }
         }
+        if (epi == LLB_EPI_BIAS_F32) {
+          // fp32 output: thread == row writes its 32 consecutive columns (one full 128-byte line)
+          const int grow = row_base + lane;
+          if (grow < p.M) {
+            float* orow = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(grow) * p.ldo + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (col0 + g * 4 < p.N) {
+                const float4 b4 = *reinterpret_cast<const float4*>(my_bias + c * 32 + g * 4);
+                float4 o4 = make_float4(__uint_as_float(v[g * 4]) + b4.x, __uint_as_float(v[g * 4 + 1]) + b4.y,
+                                        __uint_as_float(v[g * 4 + 2]) + b4.z, __uint_as_float(v[g * 4 + 3]) + b4.w);
+                if constexpr (kFp8) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(my_ws + c * 32 + g * 4);
+                  o4 = make_float4(__uint_as_float(v[g * 4]) * w4.x * row_scale + b4.x,
+                                   __uint_as_float(v[g * 4 + 1]) * w4.y * row_scale + b4.y,
+                                   __uint_as_float(v[g * 4 + 2]) * w4.z * row_scale + b4.z,
+                                   __uint_as_float(v[g * 4 + 3]) * w4.w * row_scale + b4.w);
+                }
+                *reinterpret_cast<float4*>(orow + g * 4) = o4;
+              }
+            }
+          }
+          continue;
+        }
         // phase 1: thread == row.  bias (+activation) -> bf16 -> staging row (64 bytes, 4 chunks)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -432,11 +456,12 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   LLB_CHECK_ARG(A && W && out, "gemm: null tensor");
   LLB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   LLB_CHECK_ARG(K % (fp8 ? 16 : 8) == 0 && N % 8 == 0, "gemm: K / N alignment (K=%d N=%d)", K, N);
-  LLB_CHECK_ARG(lda % (fp8 ? 16 : 8) == 0 && ldw % (fp8 ? 16 : 8) == 0 && ldo % 8 == 0,
+  LLB_CHECK_ARG(lda % (fp8 ? 16 : 8) == 0 && ldw % (fp8 ? 16 : 8) == 0 && (ldo % 8 == 0 || epilogue == LLB_EPI_BIAS_F32),
                 "gemm: leading dims must be 16-byte multiples");
   LLB_CHECK_ARG(!fp8 || (a_scale && w_scale && (reinterpret_cast<uintptr_t>(w_scale) & 15) == 0),
                 "gemm_fp8: needs a_scale[M] and a 16-byte aligned w_scale[N]");
-  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_RES, "gemm: unknown epilogue %d", epilogue);
+  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_F32, "gemm: unknown epilogue %d", epilogue);
+  LLB_CHECK_ARG(epilogue != LLB_EPI_BIAS_F32 || ldo % 4 == 0, "gemm: fp32 output needs ldo %% 4 == 0");
   if (epilogue == LLB_EPI_BIAS_GATE_RES) {
     LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
                   "gemm: gate/residual epilogue needs gate, res, rows_per_gate");

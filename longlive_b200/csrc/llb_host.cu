@@ -93,6 +93,33 @@ int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
   return LLB_OK;
 }
 
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint64_t H, uint64_t W,
+                      uint64_t C, uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    return LLB_E_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (C * 2) % 16 != 0) {
+    set_error("tensor map (4d): base/stride must be 16-byte aligned (base=%p C=%llu)", base, (unsigned long long)C);
+    return LLB_E_INVALID;
+  }
+  cuuint64_t gdim[4] = {C, W, H, frames};
+  cuuint64_t gstride[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (CUresult %d) frames=%llu H=%llu W=%llu C=%llu box=%ux%ux%u",
+              (int)r, (unsigned long long)frames, (unsigned long long)H, (unsigned long long)W,
+              (unsigned long long)C, box_h, box_w, box_c);
+    return LLB_E_CUDA;
+  }
+  return LLB_OK;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     // Off unless LLB_PDL=1: measured neutral on the 21-frame bench (93.9 vs 93.5 FPS, the forward runs

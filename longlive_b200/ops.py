@@ -12,14 +12,14 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_SILU,
+from ._lib import (EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_SILU,
                    STEP_PARAMS_INT32, StepParams)
 
 __all__ = [
     "gemm", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
     "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
     "build_rope_table", "launch_count",
-    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES",
+    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES", "EPI_BIAS_F32",
 ]
 
 
@@ -49,14 +49,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0, gate_row0: int = 0,
          res: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  a/w/out 2-D bf16 (row stride arbitrary)."""
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  a/w/out 2-D bf16 (row stride arbitrary);
+    with EPI_BIAS_F32 the output is float32."""
     _req(a, "a"); _req(w, "w")
     M, K = a.shape
     N, K2 = w.shape
     assert K == K2, (a.shape, w.shape)
+    out_dtype = torch.float32 if epilogue == EPI_BIAS_F32 else torch.bfloat16
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-    _req(out, "out")
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _req(out, "out", out_dtype)
     for t, n in ((bias, "bias"), (gate, "gate"), (res, "res")):
         if t is not None:
             _req(t, n)

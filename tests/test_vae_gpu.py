@@ -1,0 +1,129 @@
+"""Streaming VAE decoder on libllb200 (longlive_b200/vae.py) against the oracle restatement of the reference
+decoder (oracle/vae_oracle.py, itself pinned bit-for-bit to the reference module) and against the committed
+outputs of the reference module (tests/golden/vae_small.pt)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "vae_small.pt")
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _cl(x):  # [C, T, H, W] -> channels-last [T, H, W, C]
+    return x.permute(1, 2, 3, 0).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W", [(64, 64, (3, 3, 3), 5, 7), (128, 192, (3, 3, 3), 24, 40), (64, 128, (1, 3, 3), 17, 33),
+                                            (192, 64, (3, 1, 1), 9, 16), (64, 64, (1, 1, 1), 8, 16), (384, 384, (3, 3, 3), 12, 20)])
+def test_conv3d_matches_torch_with_ring_history(cin, cout, k, H, W):
+    """Two consecutive calls (T = 2 then T = 3) on a 5-frame ring: the second call's temporal taps must see the
+    first call's last frames through the ring (wrap-around included), exactly like CausalConv3d with its cache."""
+    from longlive_b200 import vae
+    g = torch.Generator().manual_seed(cin + cout + H)
+    kt, kh, kw = k
+    w = (torch.randn(cout, cin, kt, kh, kw, generator=g) / (cin * kt * kh * kw) ** 0.5).to(torch.bfloat16)
+    b = (0.1 * torch.randn(cout, generator=g)).to(torch.bfloat16)
+    wp = w.permute(0, 2, 3, 4, 1).reshape(cout, -1).contiguous().to(DEV)
+    frames = [torch.randn(cin, 1, H, W, generator=g).to(torch.bfloat16) for _ in range(5)]
+    ring = vae.FrameRing(5, H, W, cin, DEV)
+    stream = torch.zeros(cin, 2, H, W, dtype=torch.bfloat16)  # two zero frames = causal padding
+    done = 0
+    for T in (2, 3):
+        new = torch.cat(frames[done:done + T], 1)
+        t0 = ring.reserve(T)
+        for i in range(T):
+            ring.buf[(t0 + i) % 5].copy_(_cl(new[:, i:i + 1])[0])
+        res = torch.randn(T, H, W, cout, generator=g).to(torch.bfloat16).to(DEV)
+        out = torch.full((T, H, W, cout), 3.0, dtype=torch.bfloat16, device=DEV)
+        vae.conv3d(ring.buf, t0, wp, b.to(DEV), k, out, T, res=res)
+        stream = torch.cat([stream, new], 1)
+        xin = stream[:, -(T + kt - 1):] if kt == 3 else new
+        ref = F.conv3d(F.pad(xin.float().unsqueeze(0), (kw // 2, kw // 2, kh // 2, kh // 2, 0, 0)), w.float(), b.float())[0]
+        ref = _cl(ref.to(torch.bfloat16)).float() + res.cpu().float()
+        err = rel_l2(out.cpu(), ref)
+        assert err < 4e-3, f"T={T}: rel-L2 {err}"
+        done += T
+
+
+@pytest.mark.parametrize("C,silu", [(16, True), (96, True), (192, False), (384, True)])
+def test_vae_norm_matches_reference_op_chain(C, silu):
+    from longlive_b200 import vae
+    from oracle import vae_oracle as vo
+    g = torch.Generator().manual_seed(C)
+    Cp = (C + 63) // 64 * 64
+    x = torch.randn(1, C, 2, 9, 11, generator=g).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(C, 1, 1, 1, generator=g)).to(torch.bfloat16)
+    ref = vo.rms_norm(x, gamma)
+    if silu:
+        ref = F.silu(ref)
+    xin = torch.zeros(2, 9, 11, Cp, dtype=torch.bfloat16)
+    xin[..., :C] = _cl(x[0])
+    gp = torch.zeros(Cp, dtype=torch.bfloat16); gp[:C] = gamma.reshape(-1)
+    out = torch.empty(2, 9, 11, Cp, dtype=torch.bfloat16, device=DEV)
+    vae.vae_norm(xin.to(DEV), 0, out, 0, 2, C, gp.to(DEV), silu)
+    got = out.cpu()
+    assert got[..., C:].abs().max().item() == 0 if Cp > C else True
+    diff = (got[..., :C].float() - _cl(ref[0]).float()).abs()
+    # same rounding chain: identical up to 1 bf16 ulp where the fp32 norm / exp differ in the last bit
+    assert (diff <= _cl(ref[0]).float().abs() * 2 ** -7 + 1e-6).all()
+    assert (diff == 0).float().mean().item() > 0.98
+
+
+def _decoder(cfg_kwargs, sd):
+    from longlive_b200.vae import WanVAEDecoder
+    dec = WanVAEDecoder(dim=cfg_kwargs["dim"], z_dim=cfg_kwargs["z_dim"], dim_mult=cfg_kwargs["dim_mult"],
+                        num_res_blocks=cfg_kwargs["num_res_blocks"], temporal_upsample=cfg_kwargs["temporal_upsample"])
+    dec.load_state_dict(sd)
+    return dec.to(DEV)
+
+
+def test_small_decoder_streaming_vs_reference_golden_and_oracle():
+    from oracle import vae_oracle as vo
+    from oracle.make_vae_golden import latents, scale_of
+    gold = torch.load(GOLDEN)
+    cfg = vo.VaeConfig(**gold["cfg"])
+    sd = vo.init_state_dict(cfg, seed=gold["seed"], dtype=torch.bfloat16)
+    dec = _decoder(gold["cfg"], sd)
+    scale = [s.to(DEV) for s in scale_of(cfg, torch.bfloat16)]
+    for i, t in enumerate(gold["chunks"]):
+        z = latents(cfg, 10 + i, t).to(torch.bfloat16).to(DEV)
+        out = dec.cached_decode(z, scale).cpu()
+        ref = gold["bf16"]["stream"][i].float().clamp(-1, 1)        # the reference module's own output
+        exact = gold["f32"]["stream"][i].float().clamp(-1, 1)
+        assert out.shape == ref.shape
+        e_ref, e_exact, floor = rel_l2(out, ref), rel_l2(out, exact), rel_l2(ref, exact)
+        print(f"call {i}: vs reference bf16 {e_ref:.3e}, vs fp32 {e_exact:.3e} (reference bf16 vs fp32 {floor:.3e})")
+        assert e_ref < 2e-2 and e_exact < 1.5 * floor + 5e-3
+    whole = dec.decode(latents(cfg, 99, 4).to(torch.bfloat16).to(DEV), scale).cpu()
+    assert rel_l2(whole, gold["bf16"]["whole"].float().clamp(-1, 1)) < 2e-2
+
+
+def test_decode_to_pixel_wrapper_and_cache_reset():
+    from oracle import vae_oracle as vo
+    from oracle.make_vae_golden import SMALL, latents
+    from longlive_b200.vae import WanVAEWrapper
+    cfg = vo.VaeConfig(**SMALL)
+    sd = vo.init_state_dict(cfg, seed=3, dtype=torch.bfloat16)
+    wrap = WanVAEWrapper(_decoder(SMALL, sd))
+    oracle = vo.VaeDecoderOracle(cfg, sd)
+    lat = latents(cfg, 21, 3).permute(0, 2, 1, 3, 4).to(torch.bfloat16)          # [B, T, z, h, w]
+    a = wrap.decode_to_pixel(lat.to(DEV), use_cache=False)
+    b = wrap.decode_to_pixel(lat.to(DEV), use_cache=False)                      # decode() must leave no state behind
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        ref = oracle.decode_to_pixel(lat, use_cache=False)
+    assert a.shape == ref.shape == (1, 9, 3, 40, 56) and a.dtype == torch.float32
+    assert rel_l2(a.cpu(), ref) < 2e-2
+    # streaming: two cached calls == one call over the concatenation
+    wrap.model.clear_cache()
+    s1 = wrap.decode_to_pixel(lat[:, :1].to(DEV), use_cache=True)
+    s2 = wrap.decode_to_pixel(lat[:, 1:].to(DEV), use_cache=True)
+    assert torch.equal(torch.cat([s1, s2], 1), a)
