@@ -8,65 +8,94 @@
 
 namespace llb {
 
-__device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_ref(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // RMS_norm.forward (vae.py:51-54) = F.normalize(x, dim=channels) * sqrt(C) * gamma (+ 0), then optionally
-// nn.SiLU: per pixel, LPP lanes x NV 16-byte vectors cover the Cp channels.
+// nn.SiLU: per pixel, LPP lanes x NV 16-byte vectors cover the Cp channels.  Each lane group handles kPix
+// pixels per pass with all their loads issued before any arithmetic (the kernel is a pure HBM stream: 2 x
+// tensor bytes, nothing to reuse), and walks the tensor with a grid stride.
+constexpr int kNormPix = 4;
 template <int LPP, int NV>
 __global__ void __launch_bounds__(256)
 vae_norm_kernel(const __nv_bfloat16* __restrict__ in, int in_frames, int in_t0, __nv_bfloat16* __restrict__ out,
-                int out_frames, int out_t0, int T, int64_t pixels, int Cp, float scale,
+                int out_frames, int out_t0, int T, int pixels, int Cp, float scale,
                 const __nv_bfloat16* __restrict__ gamma, int silu) {
   griddep_wait();
-  const int64_t gp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / LPP;  // pixel over T*pixels
   const int sub = threadIdx.x % LPP;
-  const bool live = gp < static_cast<int64_t>(T) * pixels;
-  const int t = live ? static_cast<int>(gp / pixels) : 0;
-  const int64_t px = live ? gp - static_cast<int64_t>(t) * pixels : 0;
   const int nvec = Cp / 8;
-  const uint4* src = reinterpret_cast<const uint4*>(in + (static_cast<int64_t>((in_t0 + t) % in_frames) * pixels + px) * Cp);
-  uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>((out_t0 + t) % out_frames) * pixels + px) * Cp);
-  uint4 v[NV];
-  float ss = 0.f;
+  const int total = T * pixels;  // < 2^31 (checked on the host)
+  const int groups = (gridDim.x * blockDim.x) / LPP;
+  // gamma is the same for every pixel: keep this lane's slices in registers
+  uint4 g4[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = sub + i * LPP;
-    v[i] = make_uint4(0, 0, 0, 0);
-    if (live && vi < nvec) v[i] = src[vi];
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = bf16_lo(w[e]), b = bf16_hi(w[e]);
-      ss += a * a + b * b;
-    }
+    g4[i] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(gamma) + vi) : make_uint4(0, 0, 0, 0);
   }
+  // uniform trip count: every lane of a warp must reach the shuffles below, out-of-range groups just idle
+  const int n_iters = (total + groups * kNormPix - 1) / (groups * kNormPix);
+  for (int it = 0; it < n_iters; ++it) {
+    const int base = (blockIdx.x * blockDim.x + threadIdx.x) / LPP + it * groups * kNormPix;
+    uint4 v[kNormPix][NV];
+    const uint4* src[kNormPix];
+    uint4* dst[kNormPix];
+    bool live[kNormPix];
 #pragma unroll
-  for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  // x.norm(2, dim) comes back as a bf16 tensor, clamp_min(1e-12), then the bf16 division
-  const float denom = fmaxf(bf16_round(sqrtf(ss)), 1e-12f);
+    for (int k = 0; k < kNormPix; ++k) {
+      const int gp = base + k * groups;
+      live[k] = gp < total;
+      const int t = live[k] ? gp / pixels : 0;
+      const int px = live[k] ? gp - t * pixels : 0;
+      src[k] = reinterpret_cast<const uint4*>(in + (static_cast<int64_t>((in_t0 + t) % in_frames) * pixels + px) * Cp);
+      dst[k] = reinterpret_cast<uint4*>(out + (static_cast<int64_t>((out_t0 + t) % out_frames) * pixels + px) * Cp);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = sub + i * LPP;
-    if (!(live && vi < nvec)) continue;
-    const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(gamma) + vi);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g4);
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float y[2] = {bf16_lo(w[e]), bf16_hi(w[e])};
-      const float gg[2] = {bf16_lo(gw[e]), bf16_hi(gw[e])};
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float a = bf16_round(y[k] / denom);
-        a = bf16_round(a * scale);
-        a = bf16_round(a * gg[k]);
-        if (silu) a = silu_ref(a);
-        y[k] = a;
+      for (int i = 0; i < NV; ++i) {
+        const int vi = sub + i * LPP;
+        v[k][i] = (live[k] && vi < nvec) ? src[k][vi] : make_uint4(0, 0, 0, 0);
       }
-      o[e] = pack_bf16x2(y[0], y[1]);
     }
-    dst[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < kNormPix; ++k) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[k][i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = bf16_lo(w[e]), b = bf16_hi(w[e]);
+          ss += a * a + b * b;
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      // x.norm(2, dim) comes back as a bf16 tensor, clamp_min(1e-12), then the bf16 division
+      // (one exact reciprocal per pixel; x * (1/d) and x / d can differ in the last fp32 bit, which survives
+      // the following bf16 rounding for about one element in 2^15)
+      const float inv = __frcp_rn(fmaxf(bf16_round(sqrtf(ss)), 1e-12f));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = sub + i * LPP;
+        if (!(live[k] && vi < nvec)) continue;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[k][i]);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g4[i]);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float y[2] = {bf16_lo(w[e]), bf16_hi(w[e])};
+          const float gg[2] = {bf16_lo(gw[e]), bf16_hi(gw[e])};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float a = bf16_round(y[q] * inv);
+            a = bf16_round(a * scale);
+            a = bf16_round(a * gg[q]);
+            if (silu) a = silu_ref(a);
+            y[q] = a;
+          }
+          o[e] = pack_bf16x2(y[0], y[1]);
+        }
+        dst[k][vi] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
 }
 
@@ -175,19 +204,23 @@ extern "C" int llb_vae_norm(const void* in, int in_frames, int in_t0, void* out,
                             int64_t pixels, int Cp, int C, const void* gamma, int silu, void* stream) {
   LLB_CHECK_ARG(in && out && gamma && T > 0 && pixels > 0 && in_frames >= T && out_frames >= T, "vae_norm: bad arguments");
   LLB_CHECK_ARG(Cp % 64 == 0 && Cp <= 512 && C > 0 && C <= Cp, "vae_norm: Cp=%d C=%d unsupported", Cp, C);
+  LLB_CHECK_ARG(static_cast<int64_t>(T) * pixels < (1ll << 30), "vae_norm: too many pixels");
   const float scale = sqrtf(static_cast<float>(C));  // python float dim ** 0.5, used as an fp32 scalar
   const int nvec = Cp / 8;
   const int lpp = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
-  const int64_t threads = static_cast<int64_t>(T) * pixels * lpp;
-  const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
+  const int64_t groups = (static_cast<int64_t>(T) * pixels + kNormPix - 1) / kNormPix;
+  const int64_t blocks = (groups * lpp + 255) / 256;
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+  const unsigned grid = static_cast<unsigned>(blocks < static_cast<int64_t>(sms) * 16 ? blocks : sms * 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const auto* i = static_cast<const __nv_bfloat16*>(in);
   auto* o = static_cast<__nv_bfloat16*>(out);
   const auto* g = static_cast<const __nv_bfloat16*>(gamma);
-  if (lpp == 8) vae_norm_kernel<8, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, pixels, Cp, scale, g, silu);
-  else if (lpp == 16) vae_norm_kernel<16, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, pixels, Cp, scale, g, silu);
-  else if (nvec <= 32) vae_norm_kernel<32, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, pixels, Cp, scale, g, silu);
-  else vae_norm_kernel<32, 2><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, pixels, Cp, scale, g, silu);
+  const int px = static_cast<int>(pixels);
+  if (lpp == 8) vae_norm_kernel<8, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, px, Cp, scale, g, silu);
+  else if (lpp == 16) vae_norm_kernel<16, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, px, Cp, scale, g, silu);
+  else if (nvec <= 32) vae_norm_kernel<32, 1><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, px, Cp, scale, g, silu);
+  else vae_norm_kernel<32, 2><<<grid, 256, 0, s>>>(i, in_frames, in_t0, o, out_frames, out_t0, T, px, Cp, scale, g, silu);
   LLB_LAUNCH_CHECK("vae_norm_kernel");
   return LLB_OK;
 }
