@@ -238,20 +238,23 @@ int llb_silu(const void* x, void* out, int64_t n, void* stream);
  * the zero padding at the start of a stream.
  * ------------------------------------------------------------------------------------------ */
 typedef struct llb_conv3d_desc {
-  const void* in;       /* [in_frames, H, W, Cin] bf16 ring */
+  const void* in;       /* [in_frames, H, W, ld_in] bf16 ring */
   int in_frames, in_t0; /* ring length; ring index of the first new frame */
-  int H, W, Cin, Cout;  /* Cin, Cout: padded, multiples of 64 */
+  int H, W;
+  int Cin, ld_in;       /* channels convolved (multiple of 32) and the channel stride of `in` (>= Cin) */
+  int Cout, ld_out;     /* channels produced (multiple of 32) and the channel stride of `out` / `res`;
+                           columns [Cout, ld_out) are left untouched */
   const void* weight;   /* [Cout, kt*kh*kw*Cin] bf16: tap-major, k = ((dt*kh + dh)*kw + dw)*Cin + c */
   const void* bias;     /* [Cout] bf16 or NULL */
   int kt, kh, kw;       /* 3x3x3, 3x1x1, 1x3x3 or 1x1x1; causal in t, zero "same" padding in h / w */
-  void* out;            /* [out_frames, H, W, Cout] bf16; frame t goes to ring index (out_t0 + t*out_t_step) % out_frames */
+  void* out;            /* [out_frames, H, W, ld_out] bf16; frame t goes to ring index (out_t0 + t*out_t_step) % out_frames */
   int out_frames, out_t0, out_t_step;
-  const void* res;      /* optional [res_frames, H, W, Cout]: out = bf16(res + bf16(conv + bias)); may alias out */
+  const void* res;      /* optional [res_frames, H, W, ld_out]: out = bf16(res + bf16(conv + bias)); may alias out */
   int res_frames, res_t0;
   int T;                /* frames to produce */
 } llb_conv3d_desc;
 /* CausalConv3d.forward (vae.py:28-36) / the per-frame nn.Conv2d of Resample (vae.py:76-83) as an implicit
- * GEMM on tcgen05: TMA loads one shifted [8 x 16 pixel x 64 channel] box per (tap, channel chunk). */
+ * GEMM on tcgen05: TMA loads one shifted [8 x 16 pixel x 64 (or 32) channel] box per (tap, channel chunk). */
 int llb_conv3d(const llb_conv3d_desc* d, void* stream);
 /* RMS_norm.forward (vae.py:51-54) over the C real channels of every pixel, optionally followed by SiLU
  * (the RMS_norm -> SiLU pairs of ResidualBlock / head, vae.py:193-199, 415-417); gamma [Cp] bf16, 0 in the pad. */

@@ -97,7 +97,8 @@ class Conv3dDesc(C.Structure):
     """llb_conv3d_desc (include/llb200.h): one causal convolution over channels-last frame rings."""
 
     _fields_ = [("inp", C.c_void_p), ("in_frames", C.c_int), ("in_t0", C.c_int),
-                ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("ld_in", C.c_int),
+                ("Cout", C.c_int), ("ld_out", C.c_int),
                 ("weight", C.c_void_p), ("bias", C.c_void_p),
                 ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int),
                 ("out", C.c_void_p), ("out_frames", C.c_int), ("out_t0", C.c_int), ("out_t_step", C.c_int),

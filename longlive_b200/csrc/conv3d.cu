@@ -24,28 +24,37 @@
 namespace llb {
 
 constexpr int kConvTH = 8, kConvTW = 16;  // pixel patch = 128 GEMM rows
-constexpr int kConvBK = 64;
 constexpr int kConvEpiWarps = 8;
 constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
 constexpr int kConvEpiStageBytesPerWarp = 32 * 64;
 
-template <int BN>
+// BN: output channels per tile (64 / 96 / 128 / 192).  CK: channels per k-block: 64 (128-byte swizzle rows) or
+// 32 (64-byte rows) - the latter for layers whose channel count is a multiple of 32 only (the 96-channel
+// full-resolution stage), so that no zero padding is moved or multiplied.
+// CPS: channel chunks per pipeline stage - with 32-channel chunks one k-block is only two short MMAs, too
+// little work per barrier round trip, so a stage then carries all three chunks of a 96-channel tap.
+template <int BN, int CK, int CPS>
 struct ConvCfg {
-  static constexpr int kStageA = 128 * kConvBK * 2;
-  static constexpr int kStageB = BN * kConvBK * 2;
+  static constexpr int kChunkA = 128 * CK * 2;
+  static constexpr int kChunkB = BN * CK * 2;
+  static constexpr int kStageA = CPS * kChunkA;
+  static constexpr int kStageB = CPS * kChunkB;
   static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kEpiVecBytesPerWarp = (BN / 2) * 4;
+  static constexpr int kSlabs = BN / 32;                      // 32-column epilogue slabs, dealt out alternately
+  static constexpr int kEpiVecBytesPerWarp = ((kSlabs + 1) / 2) * 32 * 4;
   static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp);
   static constexpr int kFixedBytes = 1024 + kEpiBytes + 256;
   static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kStages = kStagesFit > 12 ? 12 : kStagesFit;
+  static_assert(2 * kStages + 5 <= 32, "barrier block is 256 bytes");
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
   static_assert(kStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct ConvParams {
-  int H, W, Cin, Cout, T;
+  int H, W, Cin, Cout, T;  // Cin: channels iterated per tap (multiple of CK); Cout: channels produced
+  int ld_out;              // channel stride of out / res (>= Cout)
   int kt, kh, kw;
   int in_frames, in_t0;
   __nv_bfloat16* out;
@@ -56,11 +65,11 @@ struct ConvParams {
   int tiles_h, tiles_w, num_n_tiles;
 };
 
-template <int BN>
+template <int BN, int CK, int CPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
               const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, CK, CPS>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,7 +91,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   const int tiles_per_frame = p.tiles_h * p.tiles_w;
   const int num_m_tiles = p.T * tiles_per_frame;
   const int num_tiles = num_m_tiles * p.num_n_tiles;
-  const int cchunks = p.Cin / kConvBK;
+  const int cchunks = p.Cin / (CK * CPS);  // chunk groups (= pipeline stages) per tap
   const int taps = p.kt * p.kh * p.kw;
   const int num_kb = taps * cchunks;
 
@@ -133,9 +142,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
                 const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
                 const uint32_t sb = sa + Cfg::kStageA;
                 mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                tma_load_4d(sa, &tmap_in, full_bar(stage), cc * kConvBK, w0 + dw - p.kw / 2,
-                            h0 + dh - p.kh / 2, tin);
-                tma_load_2d(sb, &tmap_w, full_bar(stage), tap * p.Cin + cc * kConvBK, n_idx * BN);
+#pragma unroll
+                for (int j = 0; j < CPS; ++j) {
+                  const int c0 = (cc * CPS + j) * CK;
+                  tma_load_4d(sa + j * Cfg::kChunkA, &tmap_in, full_bar(stage), c0, w0 + dw - p.kw / 2,
+                              h0 + dh - p.kh / 2, tin);
+                  tma_load_2d(sb + j * Cfg::kChunkB, &tmap_w, full_bar(stage), tap * p.Cin + c0, n_idx * BN);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
             }
@@ -160,11 +173,15 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
         tc_fence_after();
         const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
         const uint32_t sb = sa + Cfg::kStageA;
-        const uint64_t da = umma_desc_kmajor(sa);
-        const uint64_t db = umma_desc_kmajor(sb);
+        const uint64_t da = CK == 64 ? umma_desc_kmajor(sa) : umma_desc_kmajor_sw64(sa);
+        const uint64_t db = CK == 64 ? umma_desc_kmajor(sb) : umma_desc_kmajor_sw64(sb);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kConvBK / 16; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int j = 0; j < CPS; ++j)
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k)
+              umma_ss(d_tmem, da + j * (Cfg::kChunkA >> 4) + 2 * k, db + j * (Cfg::kChunkB >> 4) + 2 * k, idesc,
+                      (kb | j | k) != 0);
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
         }
@@ -193,7 +210,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 #pragma unroll
-      for (int i = 0; i < BN / 64; ++i) {
+      for (int i = 0; 2 * i + h < Cfg::kSlabs; ++i) {
         const int cg = n_idx * BN + (2 * i + h) * 32 + lane;
         my_bias[i * 32 + lane] = (p.bias != nullptr && cg < p.Cout) ? __bfloat162float(p.bias[cg]) : 0.f;
       }
@@ -202,12 +219,12 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = 0; 2 * c + h < Cfg::kSlabs; ++c) {
         const int col0 = n_idx * BN + (2 * c + h) * 32;
         uint32_t v[32];
         tmem_ld32(t_row + c * 64, v);
         tmem_wait_ld();
-        if (c == BN / 64 - 1) {
+        if (2 * (c + 1) + h >= Cfg::kSlabs) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -239,11 +256,11 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
           const int row = q * 32 + r;                     // row of the 8 x 16 patch: h-major
           const int ph = h0 + (row >> 4), pw = w0 + (row & 15);
           ok[i] = col_ok && ph < p.H && pw < p.W;
-          off[i] = (static_cast<int64_t>(ph) * p.W + pw) * p.Cout + gcol;
+          off[i] = (static_cast<int64_t>(ph) * p.W + pw) * p.ld_out + gcol;
           yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((seg ^ ((r >> 1) & 3)) << 4));
           xv[i] = make_uint4(0, 0, 0, 0);
           if (ok[i] && has_res)
-            xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(t_res) * p.H * p.W * p.Cout + off[i]);
+            xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(t_res) * p.H * p.W * p.ld_out + off[i]);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -258,7 +275,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
               o[e] = pack_bf16x2(bf16_lo(xx[e]) + bf16_lo(yy[e]), bf16_hi(xx[e]) + bf16_hi(yy[e]));
             y = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(t_out) * p.H * p.W * p.Cout + off[i]) = y;
+          *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(t_out) * p.H * p.W * p.ld_out + off[i]) = y;
         }
         __syncwarp();
       }
@@ -273,21 +290,32 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   }
 }
 
-template <int BN>
+template <int BN, int CK, int CPS>
 static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, CK, CPS>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
     attr_set = true;
   }
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.T * p.tiles_h * p.tiles_w * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv3d_kernel<BN><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
+  conv3d_kernel<BN, CK, CPS><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
   LLB_LAUNCH_CHECK("conv3d_kernel");
   return LLB_OK;
+}
+
+template <int CK, int CPS>
+static int dispatch_conv(int bn, const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t s) {
+  switch (bn) {
+    case 192: return launch_conv<192, CK, CPS>(ti, tw, p, s);
+    case 128: return launch_conv<128, CK, CPS>(ti, tw, p, s);
+    case 96: return launch_conv<96, CK, CPS>(ti, tw, p, s);
+    default: return launch_conv<64, CK, CPS>(ti, tw, p, s);
+  }
 }
 
 }  // namespace llb
@@ -296,8 +324,11 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(d && d->in && d->weight && d->out, "conv3d: null tensor");
   LLB_CHECK_ARG(d->H > 0 && d->W > 0 && d->T > 0 && d->in_frames > 0 && d->out_frames > 0, "conv3d: bad shape");
-  LLB_CHECK_ARG(d->Cin > 0 && d->Cin % 64 == 0 && d->Cout > 0 && d->Cout % 64 == 0,
-                "conv3d: channel counts must be padded to multiples of 64 (Cin=%d Cout=%d)", d->Cin, d->Cout);
+  LLB_CHECK_ARG(d->ld_in > 0 && d->ld_in % 8 == 0 && d->ld_out > 0 && d->ld_out % 8 == 0,
+                "conv3d: channel strides must be multiples of 8 (ld_in=%d ld_out=%d)", d->ld_in, d->ld_out);
+  LLB_CHECK_ARG(d->Cin > 0 && d->Cin % 32 == 0 && d->Cin <= d->ld_in && d->Cout > 0 && d->Cout % 32 == 0 &&
+                    d->Cout <= d->ld_out,
+                "conv3d: channel counts must be multiples of 32 within the strides (Cin=%d Cout=%d)", d->Cin, d->Cout);
   LLB_CHECK_ARG((d->kt == 1 || d->kt == 3) && (d->kh == 1 || d->kh == 3) && d->kw == d->kh,
                 "conv3d: kernel %dx%dx%d unsupported", d->kt, d->kh, d->kw);
   LLB_CHECK_ARG(d->in_frames >= d->T + d->kt - 1, "conv3d: input ring of %d frames too short for T=%d, kt=%d",
@@ -306,9 +337,11 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   LLB_CHECK_ARG(d->res == nullptr || d->res_frames >= d->T, "conv3d: residual ring too short");
   LLB_CHECK_ARG(d->in != d->out, "conv3d: in-place convolution is not supported");
 
-  const int bn = d->Cout % 192 == 0 ? 192 : (d->Cout % 128 == 0 ? 128 : 64);
+  const int ck = d->Cin % 64 == 0 ? 64 : 32;
+  const int bn = d->Cout % 192 == 0 ? 192 : (d->Cout % 128 == 0 ? 128 : (d->Cout % 96 == 0 ? 96 : 64));
   ConvParams p;
   p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout; p.T = d->T;
+  p.ld_out = d->ld_out;
   p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
   p.in_frames = d->in_frames; p.in_t0 = d->in_t0;
   p.out = static_cast<__nv_bfloat16*>(d->out);
@@ -318,18 +351,15 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   p.bias = static_cast<const __nv_bfloat16*>(d->bias);
   p.tiles_h = (d->H + kConvTH - 1) / kConvTH;
   p.tiles_w = (d->W + kConvTW - 1) / kConvTW;
-  p.num_n_tiles = d->Cout / bn;
+  p.num_n_tiles = (d->Cout + bn - 1) / bn;
 
   CUtensorMap ti, tw;
-  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->Cin, kConvTH, kConvTW, kConvBK);
+  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH, kConvTW, ck, 2 * ck);
   if (rc) return rc;
   const int64_t kdim = static_cast<int64_t>(d->kt) * d->kh * d->kw * d->Cin;
-  rc = make_tmap_2d_bf16(&tw, d->weight, d->Cout, kdim, kdim, bn, kConvBK);
+  rc = make_tmap_2d_bf16_sw(&tw, d->weight, d->Cout, kdim, kdim, bn, ck, 2 * ck);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 192: return launch_conv<192>(ti, tw, p, s);
-    case 128: return launch_conv<128>(ti, tw, p, s);
-    default: return launch_conv<64>(ti, tw, p, s);
-  }
+  if (ck == 64) return dispatch_conv<64, 1>(bn, ti, tw, p, s);
+  return (d->Cin / 32) % 3 == 0 ? dispatch_conv<32, 3>(bn, ti, tw, p, s) : dispatch_conv<32, 1>(bn, ti, tw, p, s);
 }

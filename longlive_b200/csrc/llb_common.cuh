@@ -282,6 +282,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
   return umma_desc_sw128(saddr, 16, 1024);
 }
+// K-major operand tile [rows][32 bf16] (64-byte rows, SWIZZLE_64B: 8-row atoms of 512 B, layout type 4).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((512u >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 // MN-major operand made of [k_rows][64 bf16] boxes (rows = K index, 128-byte rows); consecutive
 // 64-element MN blocks are `mn_block_bytes` apart, consecutive 8-row K groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t mn_block_bytes) {

@@ -56,7 +56,10 @@ int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 // 4-D channels-last activation tensor [frames, H, W, C] (bf16): box [1, box_h, box_w, box_c] with
 // 128-byte swizzle (box_c * 2 bytes must be 128); out-of-range coordinates (also negative) read as 0.
 int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint64_t H, uint64_t W,
-                      uint64_t C, uint32_t box_h, uint32_t box_w, uint32_t box_c);
+                      uint64_t C, uint32_t box_h, uint32_t box_w, uint32_t box_c, int swizzle_bytes);
+// 2-D bf16 map with a 64- or 128-byte swizzle (box_cols * 2 bytes must equal swizzle_bytes).
+int make_tmap_2d_bf16_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                         uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
 int device_sm_count();
 

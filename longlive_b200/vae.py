@@ -40,6 +40,10 @@ def _pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
+def _pad32(c: int) -> int:
+    return (c + 31) // 32 * 32
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -66,17 +70,21 @@ class FrameRing:
 
 def conv3d(inp: torch.Tensor, in_t0: int, weight: torch.Tensor, bias: Optional[torch.Tensor], k, out: torch.Tensor,
            T: int, *, out_t0: int = 0, out_t_step: int = 1, res: Optional[torch.Tensor] = None, res_t0: int = 0):
-    """llb_conv3d on channels-last rings: inp [Fi, H, W, Cin], out [Fo, H, W, Cout], weight [Cout, taps*Cin]."""
+    """llb_conv3d on channels-last rings: inp [Fi, H, W, ld_in], out [Fo, H, W, ld_out], weight [Cout, taps*Cin]
+    with Cin <= ld_in, Cout <= ld_out multiples of 32 (channels beyond them are padding and stay untouched)."""
     d = Conv3dDesc()
+    taps = k[0] * k[1] * k[2]
     d.inp, d.in_frames, d.in_t0 = inp.data_ptr(), inp.shape[0], in_t0
-    d.H, d.W, d.Cin, d.Cout = inp.shape[1], inp.shape[2], inp.shape[3], out.shape[3]
+    d.H, d.W, d.ld_in, d.ld_out = inp.shape[1], inp.shape[2], inp.shape[3], out.shape[3]
+    d.Cin, d.Cout = weight.shape[1] // taps, weight.shape[0]
     d.weight, d.bias = weight.data_ptr(), (bias.data_ptr() if bias is not None else None)
     d.kt, d.kh, d.kw = k
     d.out, d.out_frames, d.out_t0, d.out_t_step = out.data_ptr(), out.shape[0], out_t0, out_t_step
     d.res, d.res_frames, d.res_t0 = (res.data_ptr() if res is not None else None), (res.shape[0] if res is not None else 0), res_t0
     d.T = T
     assert inp.is_contiguous() and out.is_contiguous() and weight.is_contiguous()
-    assert weight.shape == (d.Cout, k[0] * k[1] * k[2] * d.Cin), (weight.shape, d.Cout, k, d.Cin)
+    assert weight.shape[1] == taps * d.Cin and d.Cin <= d.ld_in and d.Cout <= d.ld_out, (weight.shape, k, inp.shape, out.shape)
+    assert bias is None or bias.numel() == d.Cout
     _lib.check(_lib.lib().llb_conv3d(C.byref(d), _stream()), "llb_conv3d")
     return out
 
@@ -203,17 +211,18 @@ class WanVAEDecoder(nn.Module):
 
     # ---------------------------------------------------------------------------------- weight packing
     def _conv_w(self, name: str):
-        """[Cout, Cin, (kt,) kh, kw] -> ([Cout_p, taps * Cin_p] tap-major bf16, bias [Cout_p], (kt, kh, kw))."""
+        """[Cout, Cin, (kt,) kh, kw] -> ([Cout32, taps * Cin32] tap-major bf16, bias [Cout32], (kt, kh, kw)) with the
+        channel counts rounded up to multiples of 32 (zero rows / columns)."""
         if name not in self._packed:
             w, b = self._p(name + ".weight"), self._p(name + ".bias")
             if w.dim() == 4:
                 w = w.unsqueeze(2)
             cout, cin, kt, kh, kw = w.shape
-            wp = torch.zeros(_pad64(cout), kt, kh, kw, _pad64(cin), dtype=torch.bfloat16, device=w.device)
+            wp = torch.zeros(_pad32(cout), kt, kh, kw, _pad32(cin), dtype=torch.bfloat16, device=w.device)
             wp[:cout, :, :, :, :cin] = w.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
-            bp = torch.zeros(_pad64(cout), dtype=torch.bfloat16, device=w.device)
+            bp = torch.zeros(_pad32(cout), dtype=torch.bfloat16, device=w.device)
             bp[:cout] = b.to(torch.bfloat16)
-            self._packed[name] = (wp.reshape(_pad64(cout), -1).contiguous(), bp, (kt, kh, kw))
+            self._packed[name] = (wp.reshape(_pad32(cout), -1).contiguous(), bp, (kt, kh, kw))
         return self._packed[name]
 
     def _gamma(self, name: str):
@@ -253,10 +262,12 @@ class WanVAEDecoder(nn.Module):
             self._rings[key] = r
         return r
 
-    def _buf(self, key: str, shape, device, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
+    def _buf(self, key: str, shape, device, dtype=torch.bfloat16) -> torch.Tensor:
+        """Persistent scratch, zero-filled at creation: kernels only ever write the real channels / rows of a
+        buffer, so its padding stays zero for the life of the decoder."""
         b = self._scratch.get(key)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype or b.device != torch.device(device):
-            b = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+            b = torch.zeros(shape, dtype=dtype, device=device)
             self._scratch[key] = b
         return b
 
@@ -280,12 +291,12 @@ class WanVAEDecoder(nn.Module):
         rb = self._ring(p + "#b", tmax + 2, H, W, coutp, dev)
         ta, tb = ra.reserve(T), rb.reserve(T)
         vae_norm(x, 0, ra.buf, ta, T, cin, self._gamma(p + ".residual.0"), True)
-        y = self._buf(f"y{H}x{W}x{coutp}", (tmax, H, W, coutp), dev)
+        y = self._buf(f"y{H}x{W}x{coutp}c{cout}", (tmax, H, W, coutp), dev)
         self._causal_conv(p + ".residual.2", ra, ta, T, y)
         vae_norm(y, 0, rb.buf, tb, T, cout, self._gamma(p + ".residual.3"), True)
         if cin != cout:
             w, b, k = self._conv_w(p + ".shortcut")
-            h = self._buf(f"h{H}x{W}x{coutp}", (tmax, H, W, coutp), dev)
+            h = self._buf(f"h{H}x{W}x{coutp}c{cout}", (tmax, H, W, coutp), dev)
             conv3d(x, 0, w, b, k, h, T)
         else:
             h = x
@@ -302,7 +313,7 @@ class WanVAEDecoder(nn.Module):
         npad = (n + 7) // 8 * 8
         wqkv, bqkv, wo, bo = self._attn_w(p, c)
         xn = self._buf(f"an{n}x{cp}", (1, H, W, cp), dev)
-        qkv = self._buf(f"aqkv{npad}x{cp}", (npad, 3 * cp), dev, zero=True)   # rows >= n stay zero
+        qkv = self._buf(f"aqkv{npad}x{cp}", (npad, 3 * cp), dev)   # rows >= n stay zero
         logits = self._buf(f"al{n}x{npad}", (n, npad), dev, torch.float32)
         prob = self._buf(f"ap{n}x{npad}", (n, npad), dev)
         vt = self._buf(f"avt{cp}x{npad}", (cp, npad), dev)
@@ -332,15 +343,15 @@ class WanVAEDecoder(nn.Module):
                 t0 = ring.reserve(T)
                 for i in range(T):  # plain device copies: x is also the residual stream, the ring is the conv's input
                     ring.buf[(t0 + i) % ring.frames].copy_(x[i])
-                w, b, k = self._conv_w(p + ".time_conv")       # [2*cp, 3*cp]: rows [0, c) -> even frames, [c, 2c) -> odd
+                w, b, k = self._conv_w(p + ".time_conv")       # [2c, 3c]: rows [0, c) -> even frames, [c, 2c) -> odd
                 y = self._buf(f"tc{H}x{W}x{cp}", (tmax_out, H, W, cp), dev)
-                conv3d(ring.buf, t0, w[:cp], b[:cp], k, y, T, out_t0=0, out_t_step=2)
-                conv3d(ring.buf, t0, w[cp:], b[cp:], k, y, T, out_t0=1, out_t_step=2)
+                conv3d(ring.buf, t0, w[:c], b[:c], k, y, T, out_t0=0, out_t_step=2)
+                conv3d(ring.buf, t0, w[c:], b[c:], k, y, T, out_t0=1, out_t_step=2)
                 x, T = y, 2 * T
         up = self._buf(f"up{2 * H}x{2 * W}x{cp}", (tmax_out, 2 * H, 2 * W, cp), dev)
         upsample2x(x, up, T)
         w, b, k = self._conv_w(p + ".resample.1")
-        out = self._buf(f"x{2 * H}x{2 * W}x{w.shape[0]}#{p}", (tmax_out, 2 * H, 2 * W, w.shape[0]), dev)
+        out = self._buf(f"x{2 * H}x{2 * W}#{p}", (tmax_out, 2 * H, 2 * W, _pad64(c // 2)), dev)
         conv3d(up, 0, w, b, k, out, T)
         return out, T
 
@@ -361,8 +372,8 @@ class WanVAEDecoder(nn.Module):
             elif kind == "attn":
                 x = self._attn_block(p, x, T, step[2])
             elif kind == "up":
-                if step[3] and step[2] % 64 != 0:
-                    raise RuntimeError("temporal upsampling needs a channel count that is a multiple of 64")
+                if step[3] and step[2] % 32 != 0:
+                    raise RuntimeError("temporal upsampling needs a channel count that is a multiple of 32")
                 x, T = self._upsample(p, x, T, step[2], step[3], tmax)
                 if step[3]:
                     tmax *= 2

@@ -22,7 +22,9 @@ def _cl(x):  # [C, T, H, W] -> channels-last [T, H, W, C]
 
 
 @pytest.mark.parametrize("cin,cout,k,H,W", [(64, 64, (3, 3, 3), 5, 7), (128, 192, (3, 3, 3), 24, 40), (64, 128, (1, 3, 3), 17, 33),
-                                            (192, 64, (3, 1, 1), 9, 16), (64, 64, (1, 1, 1), 8, 16), (384, 384, (3, 3, 3), 12, 20)])
+                                            (192, 64, (3, 1, 1), 9, 16), (64, 64, (1, 1, 1), 8, 16), (384, 384, (3, 3, 3), 12, 20),
+                                            (96, 96, (3, 3, 3), 20, 36), (32, 96, (3, 3, 3), 9, 17), (192, 96, (1, 3, 3), 16, 32),
+                                            (96, 32, (3, 3, 3), 11, 19)])
 def test_conv3d_matches_torch_with_ring_history(cin, cout, k, H, W):
     """Two consecutive calls (T = 2 then T = 3) on a 5-frame ring: the second call's temporal taps must see the
     first call's last frames through the ring (wrap-around included), exactly like CausalConv3d with its cache."""
@@ -33,17 +35,20 @@ def test_conv3d_matches_torch_with_ring_history(cin, cout, k, H, W):
     b = (0.1 * torch.randn(cout, generator=g)).to(torch.bfloat16)
     wp = w.permute(0, 2, 3, 4, 1).reshape(cout, -1).contiguous().to(DEV)
     frames = [torch.randn(cin, 1, H, W, generator=g).to(torch.bfloat16) for _ in range(5)]
-    ring = vae.FrameRing(5, H, W, cin, DEV)
+    cinp, coutp = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64   # channel strides (padding must stay untouched)
+    ring = vae.FrameRing(5, H, W, cinp, DEV)
     stream = torch.zeros(cin, 2, H, W, dtype=torch.bfloat16)  # two zero frames = causal padding
     done = 0
     for T in (2, 3):
         new = torch.cat(frames[done:done + T], 1)
         t0 = ring.reserve(T)
         for i in range(T):
-            ring.buf[(t0 + i) % 5].copy_(_cl(new[:, i:i + 1])[0])
-        res = torch.randn(T, H, W, cout, generator=g).to(torch.bfloat16).to(DEV)
-        out = torch.full((T, H, W, cout), 3.0, dtype=torch.bfloat16, device=DEV)
+            ring.buf[(t0 + i) % 5][..., :cin].copy_(_cl(new[:, i:i + 1])[0])
+        res = torch.randn(T, H, W, coutp, generator=g).to(torch.bfloat16).to(DEV)
+        out = torch.full((T, H, W, coutp), 3.0, dtype=torch.bfloat16, device=DEV)
         vae.conv3d(ring.buf, t0, wp, b.to(DEV), k, out, T, res=res)
+        assert (out[..., cout:] == 3.0).all()
+        out, res = out[..., :cout], res[..., :cout]
         stream = torch.cat([stream, new], 1)
         xin = stream[:, -(T + kt - 1):] if kt == 3 else new
         ref = F.conv3d(F.pad(xin.float().unsqueeze(0), (kw // 2, kw // 2, kh // 2, kh // 2, 0, 0)), w.float(), b.float())[0]
