@@ -172,6 +172,38 @@ def cpu_baseline_sample():
                       f"(Lq 4680, Lk 18720), torch SDPA attention; FPS = 12 / (5 x forward time); {torch.get_num_threads()} threads"}
 
 
+def vae_decode_sample(torch, dev):
+    """Next row after the path, reported beside the headline, never folded into it:
+    steady-state streaming VAE decode of 3-latent-frame chunks at 832x480 on libllb200, random-init weights
+    of the Wan2.1 VAE shape, latents resident on the device."""
+    from longlive_b200.vae import LATENT_MEAN, LATENT_STD, WanVAEDecoder
+    dec = WanVAEDecoder()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for name, prm in dec.named_parameters():
+            if prm.dim() > 1 and not name.endswith("gamma"):
+                fan_in = prm[0].numel()
+                prm.copy_(torch.randn(prm.shape, generator=g) / fan_in ** 0.5)
+    dec = dec.to(dev)
+    scale = [torch.tensor(LATENT_MEAN).to(torch.bfloat16).to(dev), (1.0 / torch.tensor(LATENT_STD)).to(torch.bfloat16).to(dev)]
+    lat = torch.randn(1, 16, 13, 60, 104, generator=g).to(torch.bfloat16).to(dev)
+    dec.clear_cache()
+    dec.cached_decode(lat[:, :, :1], scale)
+    dec.cached_decode(lat[:, :, 1:4], scale)
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    st.record()
+    for c in range(1, 4):
+        dec.cached_decode(lat[:, :, 1 + 3 * c:4 + 3 * c], scale)
+    en.record()
+    torch.cuda.synchronize()
+    ms = st.elapsed_time(en) / 3
+    tf_per_latent = 13.55  # algorithmic TFLOP per steady-state latent frame (tools/vae_bench.py)
+    return {"ms_per_3_latent_frames": ms, "video_fps": 12e3 / ms, "tflops": 3 * tf_per_latent / ms * 1e3,
+            "what": "streaming decode (cached_decode) of 12 video frames per call at 832x480, steady state, bf16, "
+                    "Wan2.1 VAE decoder shape, random init; reference: 22 s / 240 latent frames on H100 (reports.md:37)"}
+
+
 def attention_roofline(torch, ops, dev, iters=60):
     """Dominant kernel: self-attention at the steady-state shape, timed live with CUDA events on the
     launching stream, rotating over 4 K/V sets (460 MB > L2) like consecutive layers do."""
@@ -297,6 +329,12 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    vae = None
+    if world == 1:
+        try:
+            vae = vae_decode_sample(torch, dev)
+        except Exception as e:  # informational: never fails the headline
+            vae = {"error": str(e)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -329,6 +367,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "vae_decode": vae,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

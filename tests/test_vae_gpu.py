@@ -132,3 +132,35 @@ def test_decode_to_pixel_wrapper_and_cache_reset():
     s1 = wrap.decode_to_pixel(lat[:, :1].to(DEV), use_cache=True)
     s2 = wrap.decode_to_pixel(lat[:, 1:].to(DEV), use_cache=True)
     assert torch.equal(torch.cat([s1, s2], 1), a)
+
+
+def test_pipeline_decodes_with_native_vae_full_resolution():
+    """The reference seam: CausalInferencePipeline(args, device, generator=, text_encoder=, vae=) with the
+    libllb200 VAE wrapper as `vae` - 6 latent frames at 60 x 104 -> 21 frames of 480 x 832 video in [0, 1],
+    compared with the oracle decoding the same latents with the same (small-width) decoder weights."""
+    from oracle import vae_oracle as vo
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import PIPE_CFG
+    from longlive_b200.pipeline import CausalInferencePipeline
+    from longlive_b200.vae import WanVAEWrapper
+    from longlive_b200.wrapper import WanDiffusionWrapper
+    from tests.test_model_gpu import _model_from, _pipe_args
+    cfg = wo.WanConfig(**PIPE_CFG)
+    gen = WanDiffusionWrapper(model=_model_from(cfg, wo.init_state_dict(cfg, seed=0)), timestep_shift=5.0)
+    vcfg = vo.VaeConfig(dim=32, z_dim=16)
+    vsd = vo.init_state_dict(vcfg, seed=4, dtype=torch.bfloat16)
+    vae = WanVAEWrapper(_decoder(dict(dim=32, z_dim=16, dim_mult=(1, 2, 4, 4), num_res_blocks=2,
+                                      temporal_upsample=(True, True, False)), vsd))
+    ctx = wo.synth_prompt_embeds(cfg, 200, 77).to(DEV)
+    pipe = CausalInferencePipeline(_pipe_args(cfg), torch.device(DEV), generator=gen,
+                                   text_encoder=lambda text_prompts: {"prompt_embeds": ctx}, vae=vae)
+    noise = torch.randn(1, 6, 16, 60, 104, generator=torch.Generator().manual_seed(0)).to(torch.bfloat16).to(DEV)
+    video, lat = pipe.inference(noise, text_prompts=["a"], return_latents=True)
+    assert video.shape == (1, 21, 3, 480, 832) and video.dtype == torch.float32
+    assert float(video.min()) >= 0.0 and float(video.max()) <= 1.0
+    oracle = vo.VaeDecoderOracle(vcfg, vsd).to(DEV)
+    with torch.no_grad():
+        ref = (oracle.decode_to_pixel(lat, use_cache=False) * 0.5 + 0.5).clamp(0, 1)
+    err = rel_l2(video, ref)
+    print(f"pipeline video vs oracle decode of the same latents: rel-L2 {err:.3e}")
+    assert err < 2e-2
