@@ -252,6 +252,14 @@ typedef struct llb_conv3d_desc {
   const void* res;      /* optional [res_frames, H, W, ld_out]: out = bf16(res + bf16(conv + bias)); may alias out */
   int res_frames, res_t0;
   int T;                /* frames to produce */
+  /* Optional fused RMS_norm (+SiLU) of the result (vae.py:51-54 applied to what `out` holds) into a second
+   * ring - the input of the next convolution.  Needs Cout <= 192 (one tile sees a pixel's channels);
+   * `out` may then be NULL if nobody reads the un-normalised result. */
+  void* norm_out;       /* [norm_frames, H, W, ld_out] or NULL */
+  int norm_frames, norm_t0;
+  const void* norm_gamma; /* [Cout] bf16 */
+  int norm_channels;    /* real channel count C: the result is scaled by sqrt(C) */
+  int norm_silu;
 } llb_conv3d_desc;
 /* CausalConv3d.forward (vae.py:28-36) / the per-frame nn.Conv2d of Resample (vae.py:76-83) as an implicit
  * GEMM on tcgen05: TMA loads one shifted [8 x 16 pixel x 64 (or 32) channel] box per (tap, channel chunk). */

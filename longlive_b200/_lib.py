@@ -103,7 +103,9 @@ class Conv3dDesc(C.Structure):
                 ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int),
                 ("out", C.c_void_p), ("out_frames", C.c_int), ("out_t0", C.c_int), ("out_t_step", C.c_int),
                 ("res", C.c_void_p), ("res_frames", C.c_int), ("res_t0", C.c_int),
-                ("T", C.c_int)]
+                ("T", C.c_int),
+                ("norm_out", C.c_void_p), ("norm_frames", C.c_int), ("norm_t0", C.c_int),
+                ("norm_gamma", C.c_void_p), ("norm_channels", C.c_int), ("norm_silu", C.c_int)]
 
 
 _PROTOS = {

@@ -42,8 +42,10 @@ struct ConvCfg {
   static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSlabs = BN / 32;                      // 32-column epilogue slabs, dealt out alternately
-  static constexpr int kEpiVecBytesPerWarp = ((kSlabs + 1) / 2) * 32 * 4;
-  static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp);
+  static constexpr int kMySlabs = (kSlabs + 1) / 2;          // most slabs one epilogue warp handles
+  static constexpr int kEpiVecBytesPerWarp = 2 * kMySlabs * 32 * 4;  // fp32 bias and norm gamma of its slabs
+  static constexpr int kNormXchgBytes = 2 * 8 * 32 * 4;      // per-row sums of squares, double-buffered by tile parity
+  static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp) + kNormXchgBytes;
   static constexpr int kFixedBytes = 1024 + kEpiBytes + 256;
   static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 12 ? 12 : kStagesFit;
@@ -63,9 +65,18 @@ struct ConvParams {
   int res_frames, res_t0;
   const __nv_bfloat16* bias;
   int tiles_h, tiles_w, num_n_tiles;
+  // fused RMS_norm (+SiLU) of the result into a second ring (kNorm kernels; requires one n-tile)
+  __nv_bfloat16* norm_out;
+  int norm_frames, norm_t0, norm_silu;
+  float norm_scale;  // sqrt(real channel count)
+  const __nv_bfloat16* norm_gamma;
 };
 
-template <int BN, int CK, int CPS>
+// kNorm: the epilogue additionally writes RMS_norm(result) (* gamma, optionally SiLU) into a second ring -
+// the input of the NEXT convolution - so the normalisation costs no pass over HBM of its own.  The two
+// epilogue warps of a TMEM lane quadrant each see half of a pixel's channels; they exchange their partial
+// sums of squares through shared memory and a 64-thread named barrier.
+template <int BN, int CK, int CPS, bool kNorm>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
               const ConvParams p) {
@@ -193,10 +204,15 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
+    constexpr int kMySlabs = Cfg::kMySlabs;
     uint8_t* my_stage = epi_gen + (warp - 2) * kConvEpiStageBytesPerWarp;
     float* my_bias = reinterpret_cast<float*>(epi_gen + kConvEpiWarps * kConvEpiStageBytesPerWarp +
                                               (warp - 2) * Cfg::kEpiVecBytesPerWarp);
+    float* my_gamma = my_bias + kMySlabs * 32;
+    float* xchg = reinterpret_cast<float*>(epi_gen + kConvEpiWarps * (kConvEpiStageBytesPerWarp + Cfg::kEpiVecBytesPerWarp));
     const bool has_res = p.res != nullptr;
+    const bool has_out = p.out != nullptr;
+    const int seg = lane & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_idx = tile % num_m_tiles;
@@ -210,16 +226,31 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
 #pragma unroll
-      for (int i = 0; 2 * i + h < Cfg::kSlabs; ++i) {
+      for (int i = 0; i < kMySlabs; ++i) {
         const int cg = n_idx * BN + (2 * i + h) * 32 + lane;
-        my_bias[i * 32 + lane] = (p.bias != nullptr && cg < p.Cout) ? __bfloat162float(p.bias[cg]) : 0.f;
+        const bool in = 2 * i + h < Cfg::kSlabs && cg < p.Cout;
+        my_bias[i * 32 + lane] = (in && p.bias != nullptr) ? __bfloat162float(p.bias[cg]) : 0.f;
+        if constexpr (kNorm) my_gamma[i * 32 + lane] = in ? __bfloat162float(p.norm_gamma[cg]) : 0.f;
       }
       __syncwarp();
+      // pixel of each of the four rows this lane handles in the transposed (coalesced) phase
+      int64_t pix[4];
+      bool row_ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = q * 32 + i * 8 + (lane >> 2);  // row of the 8 x 16 patch: h-major
+        const int ph = h0 + (row >> 4), pw = w0 + (row & 15);
+        row_ok[i] = ph < p.H && pw < p.W;
+        pix[i] = static_cast<int64_t>(ph) * p.W + pw;
+      }
+      uint4 yfin[kNorm ? kMySlabs : 1][4];
+      float ss[4] = {0.f, 0.f, 0.f, 0.f};
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
-#pragma unroll 1
-      for (int c = 0; 2 * c + h < Cfg::kSlabs; ++c) {
+#pragma unroll
+      for (int c = 0; c < kMySlabs; ++c) {
+        if (2 * c + h >= Cfg::kSlabs) continue;  // warp-uniform
         const int col0 = n_idx * BN + (2 * c + h) * 32;
         uint32_t v[32];
         tmem_ld32(t_row + c * 64, v);
@@ -244,27 +275,19 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
               make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
         __syncwarp();
-        const int seg = lane & 3;
         const int gcol = col0 + seg * 8;
         const bool col_ok = gcol < p.Cout;
         uint4 yv[4], xv[4];
-        int64_t off[4];
-        bool ok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + (lane >> 2);
-          const int row = q * 32 + r;                     // row of the 8 x 16 patch: h-major
-          const int ph = h0 + (row >> 4), pw = w0 + (row & 15);
-          ok[i] = col_ok && ph < p.H && pw < p.W;
-          off[i] = (static_cast<int64_t>(ph) * p.W + pw) * p.ld_out + gcol;
           yv[i] = *reinterpret_cast<const uint4*>(my_stage + r * 64 + ((seg ^ ((r >> 1) & 3)) << 4));
           xv[i] = make_uint4(0, 0, 0, 0);
-          if (ok[i] && has_res)
-            xv[i] = *reinterpret_cast<const uint4*>(p.res + static_cast<int64_t>(t_res) * p.H * p.W * p.ld_out + off[i]);
+          if (row_ok[i] && col_ok && has_res)
+            xv[i] = *reinterpret_cast<const uint4*>(p.res + (static_cast<int64_t>(t_res) * p.H * p.W + pix[i]) * p.ld_out + gcol);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (!ok[i]) continue;
           uint4 y = yv[i];
           if (has_res) {
             const uint32_t* yy = reinterpret_cast<const uint32_t*>(&yv[i]);
@@ -275,9 +298,68 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
               o[e] = pack_bf16x2(bf16_lo(xx[e]) + bf16_lo(yy[e]), bf16_hi(xx[e]) + bf16_hi(yy[e]));
             y = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(t_out) * p.H * p.W * p.ld_out + off[i]) = y;
+          const bool ok = row_ok[i] && col_ok;
+          if (ok && has_out)
+            *reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(t_out) * p.H * p.W + pix[i]) * p.ld_out + gcol) = y;
+          if constexpr (kNorm) {
+            if (!col_ok) y = make_uint4(0, 0, 0, 0);
+            yfin[c][i] = y;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = bf16_lo(w[e]), b = bf16_hi(w[e]);
+              ss[i] += a * a + b * b;
+            }
+          }
         }
         __syncwarp();
+      }
+      if constexpr (kNorm) {
+        // sum of squares of each pixel over ALL its channels: the 4 lanes sharing a row, then the partner warp
+        float* mine = xchg + ((it & 1) * 8 + q * 2 + h) * 32;
+        const float* theirs = xchg + ((it & 1) * 8 + q * 2 + (h ^ 1)) * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
+          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
+          if (seg == 0) mine[i * 8 + (lane >> 2)] = ss[i];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        float inv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          inv[i] = __frcp_rn(fmaxf(bf16_round(sqrtf(ss[i] + theirs[i * 8 + (lane >> 2)])), 1e-12f));
+        const int t_n = (p.norm_t0 + t) % p.norm_frames;
+#pragma unroll
+        for (int c = 0; c < kMySlabs; ++c) {
+          if (2 * c + h >= Cfg::kSlabs) continue;
+          const int gcol = n_idx * BN + (2 * c + h) * 32 + seg * 8;
+          if (gcol >= p.Cout) continue;
+          const float4 g0 = *reinterpret_cast<const float4*>(my_gamma + c * 32 + seg * 8);
+          const float4 g1 = *reinterpret_cast<const float4*>(my_gamma + c * 32 + seg * 8 + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!row_ok[i]) continue;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(&yfin[c][i]);
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y2[2] = {bf16_lo(w[e]), bf16_hi(w[e])};
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                float a = bf16_round(y2[k] * inv[i]);
+                a = bf16_round(a * p.norm_scale);
+                a = bf16_round(a * gg[2 * e + k]);
+                if (p.norm_silu) a = __fdividef(a, 1.0f + __expf(-a));
+                y2[k] = a;
+              }
+              o[e] = pack_bf16x2(y2[0], y2[1]);
+            }
+            *reinterpret_cast<uint4*>(p.norm_out + (static_cast<int64_t>(t_n) * p.H * p.W + pix[i]) * p.ld_out + gcol) =
+                make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
       }
     }
   }
@@ -290,12 +372,12 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   }
 }
 
-template <int BN, int CK, int CPS>
-static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+template <int BN, int CK, int CPS, bool kNorm>
+static int launch_conv_n(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, CK, CPS>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS, kNorm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -303,9 +385,15 @@ static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvP
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.T * p.tiles_h * p.tiles_w * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv3d_kernel<BN, CK, CPS><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
+  conv3d_kernel<BN, CK, CPS, kNorm><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
   LLB_LAUNCH_CHECK("conv3d_kernel");
   return LLB_OK;
+}
+
+template <int BN, int CK, int CPS>
+static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+  return p.norm_out != nullptr ? launch_conv_n<BN, CK, CPS, true>(ti, tw, p, stream)
+                               : launch_conv_n<BN, CK, CPS, false>(ti, tw, p, stream);
 }
 
 template <int CK, int CPS>
@@ -322,8 +410,9 @@ static int dispatch_conv(int bn, const CUtensorMap& ti, const CUtensorMap& tw, c
 
 extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   using namespace llb;
-  LLB_CHECK_ARG(d && d->in && d->weight && d->out, "conv3d: null tensor");
-  LLB_CHECK_ARG(d->H > 0 && d->W > 0 && d->T > 0 && d->in_frames > 0 && d->out_frames > 0, "conv3d: bad shape");
+  LLB_CHECK_ARG(d && d->in && d->weight && (d->out || d->norm_out), "conv3d: null tensor");
+  LLB_CHECK_ARG(d->H > 0 && d->W > 0 && d->T > 0 && d->in_frames > 0 && (d->out == nullptr || d->out_frames > 0),
+                "conv3d: bad shape");
   LLB_CHECK_ARG(d->ld_in > 0 && d->ld_in % 8 == 0 && d->ld_out > 0 && d->ld_out % 8 == 0,
                 "conv3d: channel strides must be multiples of 8 (ld_in=%d ld_out=%d)", d->ld_in, d->ld_out);
   LLB_CHECK_ARG(d->Cin > 0 && d->Cin % 32 == 0 && d->Cin <= d->ld_in && d->Cout > 0 && d->Cout % 32 == 0 &&
@@ -333,7 +422,8 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
                 "conv3d: kernel %dx%dx%d unsupported", d->kt, d->kh, d->kw);
   LLB_CHECK_ARG(d->in_frames >= d->T + d->kt - 1, "conv3d: input ring of %d frames too short for T=%d, kt=%d",
                 d->in_frames, d->T, d->kt);
-  LLB_CHECK_ARG(d->out_t_step >= 1 && d->out_frames >= (d->T - 1) * d->out_t_step + 1, "conv3d: output ring too short");
+  LLB_CHECK_ARG(d->out == nullptr || (d->out_t_step >= 1 && d->out_frames >= (d->T - 1) * d->out_t_step + 1),
+                "conv3d: output ring too short");
   LLB_CHECK_ARG(d->res == nullptr || d->res_frames >= d->T, "conv3d: residual ring too short");
   LLB_CHECK_ARG(d->in != d->out, "conv3d: in-place convolution is not supported");
 
@@ -345,13 +435,24 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
   p.in_frames = d->in_frames; p.in_t0 = d->in_t0;
   p.out = static_cast<__nv_bfloat16*>(d->out);
-  p.out_frames = d->out_frames; p.out_t0 = d->out_t0; p.out_t_step = d->out_t_step;
+  p.out_frames = d->out_frames > 0 ? d->out_frames : 1; p.out_t0 = d->out_t0; p.out_t_step = d->out_t_step;
   p.res = static_cast<const __nv_bfloat16*>(d->res);
   p.res_frames = d->res_frames > 0 ? d->res_frames : 1; p.res_t0 = d->res_t0;
   p.bias = static_cast<const __nv_bfloat16*>(d->bias);
   p.tiles_h = (d->H + kConvTH - 1) / kConvTH;
   p.tiles_w = (d->W + kConvTW - 1) / kConvTW;
   p.num_n_tiles = (d->Cout + bn - 1) / bn;
+  p.norm_out = static_cast<__nv_bfloat16*>(d->norm_out);
+  p.norm_frames = d->norm_frames > 0 ? d->norm_frames : 1;
+  p.norm_t0 = d->norm_t0;
+  p.norm_silu = d->norm_silu;
+  p.norm_scale = sqrtf(static_cast<float>(d->norm_channels > 0 ? d->norm_channels : 1));
+  p.norm_gamma = static_cast<const __nv_bfloat16*>(d->norm_gamma);
+  if (d->norm_out != nullptr) {
+    LLB_CHECK_ARG(p.num_n_tiles == 1, "conv3d: fused norm needs all %d output channels in one tile (<= 192)", d->Cout);
+    LLB_CHECK_ARG(d->norm_gamma && d->norm_channels > 0 && d->norm_channels <= d->Cout && d->norm_frames >= d->T &&
+                      d->norm_out != d->in, "conv3d: bad fused-norm arguments");
+  }
 
   CUtensorMap ti, tw;
   int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH, kConvTW, ck, 2 * ck);

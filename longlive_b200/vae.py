@@ -68,25 +68,38 @@ class FrameRing:
         self.pos = 0
 
 
-def conv3d(inp: torch.Tensor, in_t0: int, weight: torch.Tensor, bias: Optional[torch.Tensor], k, out: torch.Tensor,
-           T: int, *, out_t0: int = 0, out_t_step: int = 1, res: Optional[torch.Tensor] = None, res_t0: int = 0):
+def conv3d(inp: torch.Tensor, in_t0: int, weight: torch.Tensor, bias: Optional[torch.Tensor], k,
+           out: Optional[torch.Tensor], T: int, *, out_t0: int = 0, out_t_step: int = 1,
+           res: Optional[torch.Tensor] = None, res_t0: int = 0, norm: Optional[dict] = None):
     """llb_conv3d on channels-last rings: inp [Fi, H, W, ld_in], out [Fo, H, W, ld_out], weight [Cout, taps*Cin]
-    with Cin <= ld_in, Cout <= ld_out multiples of 32 (channels beyond them are padding and stay untouched)."""
+    with Cin <= ld_in, Cout <= ld_out multiples of 32 (channels beyond them are padding and stay untouched).
+    norm = {"ring": FrameRing, "t0": int, "gamma": [Cout] bf16, "C": real channels, "silu": bool} additionally
+    writes RMS_norm(result) (* gamma, SiLU) into that ring; `out` may then be None."""
     d = Conv3dDesc()
     taps = k[0] * k[1] * k[2]
     d.inp, d.in_frames, d.in_t0 = inp.data_ptr(), inp.shape[0], in_t0
-    d.H, d.W, d.ld_in, d.ld_out = inp.shape[1], inp.shape[2], inp.shape[3], out.shape[3]
+    dst = out if out is not None else norm["ring"].buf
+    d.H, d.W, d.ld_in, d.ld_out = inp.shape[1], inp.shape[2], inp.shape[3], dst.shape[3]
     d.Cin, d.Cout = weight.shape[1] // taps, weight.shape[0]
     d.weight, d.bias = weight.data_ptr(), (bias.data_ptr() if bias is not None else None)
     d.kt, d.kh, d.kw = k
-    d.out, d.out_frames, d.out_t0, d.out_t_step = out.data_ptr(), out.shape[0], out_t0, out_t_step
+    d.out, d.out_frames = (out.data_ptr(), out.shape[0]) if out is not None else (None, 0)
+    d.out_t0, d.out_t_step = out_t0, out_t_step
+    if norm is not None:
+        nb = norm["ring"].buf
+        assert nb.shape[1:] == dst.shape[1:] and nb.is_contiguous() and norm["gamma"].numel() == weight.shape[0]
+        d.norm_out, d.norm_frames, d.norm_t0 = nb.data_ptr(), nb.shape[0], norm["t0"]
+        d.norm_gamma, d.norm_channels, d.norm_silu = norm["gamma"].data_ptr(), norm["C"], int(norm["silu"])
     d.res, d.res_frames, d.res_t0 = (res.data_ptr() if res is not None else None), (res.shape[0] if res is not None else 0), res_t0
     d.T = T
-    assert inp.is_contiguous() and out.is_contiguous() and weight.is_contiguous()
+    assert inp.is_contiguous() and dst.is_contiguous() and weight.is_contiguous()
     assert weight.shape[1] == taps * d.Cin and d.Cin <= d.ld_in and d.Cout <= d.ld_out, (weight.shape, k, inp.shape, out.shape)
     assert bias is None or bias.numel() == d.Cout
     _lib.check(_lib.lib().llb_conv3d(C.byref(d), _stream()), "llb_conv3d")
     return out
+
+
+FUSED_NORM_MAX_CHANNELS = 192  # llb_conv3d's fused norm needs a pixel's channels in one tile
 
 
 def vae_norm(inp: torch.Tensor, in_t0: int, out: torch.Tensor, out_t0: int, T: int, C_real: int, gamma: torch.Tensor,
@@ -174,6 +187,7 @@ class WanVAEDecoder(nn.Module):
                     conv(p + ".time_conv", 2 * step[2], step[2], 3, 1, 1)
             else:
                 gamma(p + ".0", step[2], 3); conv(p + ".2", 3, step[2], 3, 3, 3)
+        self.fuse_norm = True  # RMS_norm + SiLU inside the producing convolution's epilogue where the tile allows
         self._packed: Dict[str, torch.Tensor] = {}
         self._rings: Dict[str, FrameRing] = {}
         self._scratch: Dict[str, torch.Tensor] = {}
@@ -233,6 +247,16 @@ class WanVAEDecoder(nn.Module):
             self._packed[name] = gp
         return self._packed[name]
 
+    def _gamma32(self, name: str):
+        """gamma padded to the conv kernels' 32-channel granularity (fused-norm argument)."""
+        key = name + "#32"
+        if key not in self._packed:
+            g = self._p(name + ".gamma").reshape(-1)
+            gp = torch.zeros(_pad32(g.numel()), dtype=torch.bfloat16, device=g.device)
+            gp[:g.numel()] = g.to(torch.bfloat16)
+            self._packed[key] = gp
+        return self._packed[key]
+
     def _attn_w(self, p: str, c: int):
         """to_qkv as one [3*Cp, Cp] GEMM weight with q | k | v row blocks each padded to Cp, and proj [Cp, Cp]."""
         key = p + "#attn"
@@ -278,22 +302,46 @@ class WanVAEDecoder(nn.Module):
         self._up_calls.clear()
 
     # ---------------------------------------------------------------------------------- the decoder
-    def _causal_conv(self, name: str, ring: FrameRing, t0: int, T: int, out: torch.Tensor, res=None):
+    def _causal_conv(self, name: str, ring: FrameRing, t0: int, T: int, out, res=None, norm=None):
         w, b, k = self._conv_w(name)
-        return conv3d(ring.buf, t0, w, b, k, out, T, res=res)
+        return conv3d(ring.buf, t0, w, b, k, out, T, res=res, norm=norm)
 
-    def _res_block(self, p: str, x: torch.Tensor, T: int, cin: int, cout: int, tmax: int) -> torch.Tensor:
-        """ResidualBlock.forward (vae.py:202-220): x [T, H, W, Cin_p] -> [T, H, W, Cout_p]."""
+    def _norm_target(self, nxt, H: int, W: int, tmax: int, T: int, c: int, dev) -> Optional[dict]:
+        """If the step after the current one starts with RMS_norm + SiLU of the current result (a residual
+        block or the head) and the channel count fits, reserve the slots of its input ring so that the current
+        step's last convolution writes the normalised frames there itself."""
+        if nxt is None or nxt[0] not in ("res", "head") or _pad32(c) > FUSED_NORM_MAX_CHANNELS or not self.fuse_norm:
+            return None
+        if nxt[0] == "res":
+            ring, gname = self._ring(nxt[1] + "#a", tmax + 2, H, W, _pad64(c), dev), nxt[1] + ".residual.0"
+        else:
+            ring, gname = self._ring(nxt[1] + "#h", tmax + 2, H, W, _pad64(c), dev), nxt[1] + ".0"
+        return {"ring": ring, "t0": ring.reserve(T), "gamma": self._gamma32(gname), "C": c, "silu": True}
+
+    def _res_block(self, p: str, x: torch.Tensor, T: int, cin: int, cout: int, tmax: int, pre=None, nxt=None) -> torch.Tensor:
+        """ResidualBlock.forward (vae.py:202-220): x [T, H, W, Cin_p] -> [T, H, W, Cout_p].  `pre`: the previous
+        convolution already left SiLU(RMS_norm(x)) in this block's input ring; `nxt`: where to leave
+        SiLU(RMS_norm(result)) for the next step."""
         dev = x.device
         _, H, W, cinp = x.shape
         coutp = _pad64(cout)
         ra = self._ring(p + "#a", tmax + 2, H, W, cinp, dev)
         rb = self._ring(p + "#b", tmax + 2, H, W, coutp, dev)
-        ta, tb = ra.reserve(T), rb.reserve(T)
-        vae_norm(x, 0, ra.buf, ta, T, cin, self._gamma(p + ".residual.0"), True)
-        y = self._buf(f"y{H}x{W}x{coutp}c{cout}", (tmax, H, W, coutp), dev)
-        self._causal_conv(p + ".residual.2", ra, ta, T, y)
-        vae_norm(y, 0, rb.buf, tb, T, cout, self._gamma(p + ".residual.3"), True)
+        if pre is None:
+            ta = ra.reserve(T)
+            vae_norm(x, 0, ra.buf, ta, T, cin, self._gamma(p + ".residual.0"), True)
+        else:
+            assert pre["ring"] is ra
+            ta = pre["t0"]
+        tb = rb.reserve(T)
+        if _pad32(cout) <= FUSED_NORM_MAX_CHANNELS and self.fuse_norm:
+            # conv1 -> RMS_norm -> SiLU in one kernel; the un-normalised conv1 output has no other reader
+            self._causal_conv(p + ".residual.2", ra, ta, T, None,
+                              norm={"ring": rb, "t0": tb, "gamma": self._gamma32(p + ".residual.3"), "C": cout, "silu": True})
+        else:
+            y = self._buf(f"y{H}x{W}x{coutp}c{cout}", (tmax, H, W, coutp), dev)
+            self._causal_conv(p + ".residual.2", ra, ta, T, y)
+            vae_norm(y, 0, rb.buf, tb, T, cout, self._gamma(p + ".residual.3"), True)
         if cin != cout:
             w, b, k = self._conv_w(p + ".shortcut")
             h = self._buf(f"h{H}x{W}x{coutp}c{cout}", (tmax, H, W, coutp), dev)
@@ -302,7 +350,7 @@ class WanVAEDecoder(nn.Module):
             h = x
         # x may be overwritten in place when the shapes agree: each output element reads its own residual first
         out = x if cin == cout else self._buf(f"x{H}x{W}x{coutp}#{p}", (tmax, H, W, coutp), dev)
-        self._causal_conv(p + ".residual.6", rb, tb, T, out, res=h)
+        self._causal_conv(p + ".residual.6", rb, tb, T, out, res=h, norm=nxt)
         return out
 
     def _attn_block(self, p: str, x: torch.Tensor, T: int, c: int) -> torch.Tensor:
@@ -330,8 +378,8 @@ class WanVAEDecoder(nn.Module):
             ops.gemm(o, wo, bo, epilogue=ops.EPI_BIAS_RES, res=xv, out=xv)
         return x
 
-    def _upsample(self, p: str, x: torch.Tensor, T: int, c: int, temporal: bool, tmax_in: int):
-        """Resample.forward, upsample2d / upsample3d (vae.py:101-138) -> (x', T')."""
+    def _upsample(self, p: str, x: torch.Tensor, T: int, c: int, temporal: bool, tmax_in: int, nxt_step=None):
+        """Resample.forward, upsample2d / upsample3d (vae.py:101-138) -> (x', T', fused-norm target or None)."""
         dev = x.device
         _, H, W, cp = x.shape
         tmax_out = 2 * tmax_in if temporal else tmax_in
@@ -352,8 +400,9 @@ class WanVAEDecoder(nn.Module):
         upsample2x(x, up, T)
         w, b, k = self._conv_w(p + ".resample.1")
         out = self._buf(f"x{2 * H}x{2 * W}#{p}", (tmax_out, 2 * H, 2 * W, _pad64(c // 2)), dev)
-        conv3d(up, 0, w, b, k, out, T)
-        return out, T
+        nxt = self._norm_target(nxt_step, 2 * H, 2 * W, tmax_out, T, c // 2, dev)
+        conv3d(up, 0, w, b, k, out, T, norm=nxt)
+        return out, T, nxt
 
     def decode_one(self, ring0: FrameRing, t0: int, out_pixels: torch.Tensor) -> int:
         """Decoder3d.forward for ONE latent frame that llb_vae_latent_in has placed at ring0[t0].
@@ -362,27 +411,38 @@ class WanVAEDecoder(nn.Module):
         _, H, W, _ = ring0.buf.shape
         T, tmax = 1, 1
         x = None
-        for step in self.plan:
+        pre = None  # fused-norm hand-over from the previous step's last convolution to this step
+        for i, step in enumerate(self.plan):
             kind, p = step[0], step[1]
+            nxt_step = self.plan[i + 1] if i + 1 < len(self.plan) else None
             if kind == "conv":
                 x = self._buf(f"x{H}x{W}x{_pad64(step[3])}#{p}", (tmax, H, W, _pad64(step[3])), dev)
-                self._causal_conv(p, ring0, t0, T, x)
+                nxt = self._norm_target(nxt_step, H, W, tmax, T, step[3], dev)
+                self._causal_conv(p, ring0, t0, T, x, norm=nxt)
+                pre = nxt
             elif kind == "res":
-                x = self._res_block(p, x, T, step[2], step[3], tmax)
+                nxt = self._norm_target(nxt_step, H, W, tmax, T, step[3], dev)
+                x = self._res_block(p, x, T, step[2], step[3], tmax, pre=pre, nxt=nxt)
+                pre = nxt
             elif kind == "attn":
                 x = self._attn_block(p, x, T, step[2])
+                pre = None
             elif kind == "up":
                 if step[3] and step[2] % 32 != 0:
                     raise RuntimeError("temporal upsampling needs a channel count that is a multiple of 32")
-                x, T = self._upsample(p, x, T, step[2], step[3], tmax)
+                x, T, pre = self._upsample(p, x, T, step[2], step[3], tmax, nxt_step)
                 if step[3]:
                     tmax *= 2
                 H, W = 2 * H, 2 * W
             else:
                 cp = x.shape[3]
                 rh = self._ring(p + "#h", tmax + 2, H, W, cp, dev)
-                th = rh.reserve(T)
-                vae_norm(x, 0, rh.buf, th, T, step[2], self._gamma(p + ".0"), True)
+                if pre is None:
+                    th = rh.reserve(T)
+                    vae_norm(x, 0, rh.buf, th, T, step[2], self._gamma(p + ".0"), True)
+                else:
+                    assert pre["ring"] is rh
+                    th = pre["t0"]
                 y = self._buf(f"head{H}x{W}", (tmax, H, W, 64), dev)
                 self._causal_conv(p + ".2", rh, th, T, y)
                 _lib.check(_lib.lib().llb_vae_pixel_out(y.data_ptr(), out_pixels.data_ptr(), T, H * W, 64, _stream()),
