@@ -217,6 +217,26 @@ def test_conv3d_fused_norm_matches_separate_norm(cin, cout, silu):
     assert nring2.buf[:T].abs().sum().item() > 0
 
 
+def test_decoder_cuda_graph_replay_matches_eager_launches():
+    from oracle import vae_oracle as vo
+    from oracle.make_vae_golden import SMALL, latents, scale_of
+    cfg = vo.VaeConfig(**SMALL)
+    sd = vo.init_state_dict(cfg, seed=6, dtype=torch.bfloat16)
+    scale = [s.to(DEV) for s in scale_of(cfg, torch.bfloat16)]
+    z = latents(cfg, 50, 16).to(torch.bfloat16).to(DEV)          # 16 frames: every graph phase replayed at least once
+    outs = []
+    for graph in (False, True):
+        dec = _decoder(SMALL, sd)
+        dec.use_cuda_graph = graph
+        a = dec.cached_decode(z[:, :, :9], scale)
+        b = dec.cached_decode(z[:, :, 9:], scale)
+        dec.clear_cache()
+        c = dec.cached_decode(z, scale)                          # second stream reuses the captured graphs
+        assert torch.equal(torch.cat([a, b], 2), c)
+        outs.append(c)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_decoder_fused_and_unfused_norm_agree():
     from oracle import vae_oracle as vo
     from oracle.make_vae_golden import SMALL, latents, scale_of
