@@ -55,7 +55,7 @@ __device__ __forceinline__ float absmax8(const uint4& v) {
 // kFp8Out: the modulated row is additionally quantised for the FP8 linear that consumes it:
 // per-row scale = amax / 448 (e4m3 max), out8 = round(y / scale); the bf16 output is skipped.
 template <bool kFp8Out, int NV>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, NV <= 6 ? 4 : 2)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                    int64_t ldo, int rows, int C, const __nv_bfloat16* __restrict__ shift,
                    const __nv_bfloat16* __restrict__ scale, int64_t ld_mod, int rows_per_frame,
@@ -81,24 +81,10 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
       for (int e = 0; e < 4; ++e) s += bf16_lo(w[e]) + bf16_hi(w[e]);
     }
   }
-  // the per-frame shift / scale (or the affine weight / bias) do not depend on the statistics:
-  // fetch them now so their latency overlaps the two warp reductions
+  // Occupancy beats prefetching here: at 64 registers four CTAs fit an SM and all 4680 rows of a chunk are
+  // in flight at once (one wave); the per-frame shift / scale vectors are L1 / L2 hits when they are needed.
   const bool affine = ln_w != nullptr;
   const int64_t mrow = static_cast<int64_t>((row0 + row) / rows_per_frame) * ld_mod;
-  uint4 av[NV], bv[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      if (affine) {
-        av[i] = __ldg(reinterpret_cast<const uint4*>(ln_w) + vi);
-        bv[i] = __ldg(reinterpret_cast<const uint4*>(ln_b) + vi);
-      } else {
-        av[i] = __ldg(reinterpret_cast<const uint4*>(scale + mrow) + vi);
-        bv[i] = __ldg(reinterpret_cast<const uint4*>(shift + mrow) + vi);
-      }
-    }
-  }
   const float mean = warp_sum(s) / static_cast<float>(C);
   float ss = 0.f;
 #pragma unroll
@@ -121,8 +107,16 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat
     const int vi = lane + i * 32;
     if (vi < nvec) {
       const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
-      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av[i]);
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv[i]);
+      uint4 a4, b4;
+      if (affine) {
+        a4 = __ldg(reinterpret_cast<const uint4*>(ln_w) + vi);
+        b4 = __ldg(reinterpret_cast<const uint4*>(ln_b) + vi);
+      } else {
+        a4 = __ldg(reinterpret_cast<const uint4*>(scale + mrow) + vi);
+        b4 = __ldg(reinterpret_cast<const uint4*>(shift + mrow) + vi);
+      }
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a4);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b4);
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -257,8 +251,11 @@ __device__ __forceinline__ int ring_dst_row(const llb_step_params* sp, int row) 
   return -1;
 }
 
+// One warp per (token row, part) with part = blockIdx.y: 0 = q, 1 = k, 2 = v.  Splitting the row three ways
+// keeps the per-thread state at one 3 KB vector set (70 registers, three CTAs per SM) instead of five, which
+// is what this latency-bound pass needs: more rows in flight, not more loads per thread.
 template <int NV>
-__global__ void __launch_bounds__(kRowWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32, 3)
 rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv,
                            __nv_bfloat16* __restrict__ q_out, int64_t ldq,
                            __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
@@ -270,83 +267,82 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
   griddep_launch_dependents();
   const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int part = blockIdx.y;
   if (row >= rows) return;
   const int nvec = C / 8;
-  const int64_t base = static_cast<int64_t>(row) * ld_qkv;
-  const uint4* qr = reinterpret_cast<const uint4*>(qkv + base);
-  const uint4* kr = reinterpret_cast<const uint4*>(qkv + base + C);
-  const uint4* vr = reinterpret_cast<const uint4*>(qkv + base + 2 * C);
-  // all of this row's traffic is issued up front: q, k, v and the two norm weights
-  uint4 qv[NV], kv[NV], vv[NV], wqv[NV], wkv[NV];
+  const int grow = sh.row0 + row;  // row in the whole chunk (token-sharded callers pass their offset)
+  const bool sharded = sh.n_ranks > 1;
+  const int dst = (part != 0 && (k_cache != nullptr || sharded)) ? ring_dst_row(sp, grow) : -1;
+  if (part != 0 && dst < 0) return;  // this token's K / V are not stored (sink re-cache rule)
+  const int vec_per_rank = sh.heads_per_rank * 16;  // 16-byte vectors per rank's head slice
+  const int64_t ldp = static_cast<int64_t>(vec_per_rank);  // peer leading dim in uint4 units
+  const uint4* src = reinterpret_cast<const uint4*>(qkv + static_cast<int64_t>(row) * ld_qkv + part * C);
+
+  if (part == 2) {
+    // V: plain copy into the ring slot (or the owner rank's ring)
+    uint4* vo = sharded ? nullptr : reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const uint4 v = src[vi];
+        if (!sharded) {
+          vo[vi] = v;
+        } else {
+          const int r = vi / vec_per_rank, lv = vi - r * vec_per_rank;
+          reinterpret_cast<uint4*>(sh.v_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = v;
+        }
+      }
+    }
+    return;
+  }
+
+  const __nv_bfloat16* wgt = part == 0 ? wq : wk;
+  uint4 xv[NV], wv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (lane + i * 32 < nvec) {
-      qv[i] = qr[lane + i * 32];
-      kv[i] = kr[lane + i * 32];
-      vv[i] = vr[lane + i * 32];
-      wqv[i] = __ldg(reinterpret_cast<const uint4*>(wq) + lane + i * 32);
-      wkv[i] = __ldg(reinterpret_cast<const uint4*>(wk) + lane + i * 32);
+      xv[i] = src[lane + i * 32];
+      wv[i] = __ldg(reinterpret_cast<const uint4*>(wgt) + lane + i * 32);
     }
   }
-  const float q_rstd = rsqrtf(row_sumsq(qv, lane, nvec) / static_cast<float>(C) + eps);
-  const float k_rstd = rsqrtf(row_sumsq(kv, lane, nvec) / static_cast<float>(C) + eps);
+  const float rstd = rsqrtf(row_sumsq(xv, lane, nvec) / static_cast<float>(C) + eps);
 
-  // token -> (frame, h, w), row-major over (frames, grid_h, grid_w); grow = row in the whole chunk
-  const int grow = sh.row0 + row;
+  // token -> (frame, h, w), row-major over (frames, grid_h, grid_w)
   const int hw = grid_h * grid_w;
   const int f = grow / hw, rem = grow - f * hw;
   const int ph = rem / grid_w, pw = rem - ph * grid_w;
   const int pf = sp->rope_start_frame + f;
-  const bool sharded = sh.n_ranks > 1;
-  const int dst = (k_cache != nullptr || sharded) ? ring_dst_row(sp, grow) : -1;
-  const int vec_per_rank = sh.heads_per_rank * 16;  // 16-byte vectors per rank's head slice
-
-  uint4* qo = reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq);
-  uint4* ko = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
-  uint4* vo = dst >= 0 && !sharded ? reinterpret_cast<uint4*>(v_cache + static_cast<int64_t>(dst) * ld_cache) : nullptr;
+  uint4* orow = part == 0 ? reinterpret_cast<uint4*>(q_out + static_cast<int64_t>(row) * ldq)
+                          : reinterpret_cast<uint4*>(k_cache + static_cast<int64_t>(dst) * ld_cache);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
       // this vector covers channels [8*vi, 8*vi+8) = complex pairs 4*(vi%16) .. +3 of head vi/16
       const int pair0 = (vi & 15) * 4;
-      const uint4 wq4 = wqv[i], wk4 = wkv[i];
-      const uint32_t* qw = reinterpret_cast<const uint32_t*>(&qv[i]);
-      const uint32_t* kw = reinterpret_cast<const uint32_t*>(&kv[i]);
-      const uint32_t* gq = reinterpret_cast<const uint32_t*>(&wq4);
-      const uint32_t* gk = reinterpret_cast<const uint32_t*>(&wk4);
-      uint32_t oq[4], ok[4];
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(&xv[i]);
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(&wv[i]);
+      uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int pi = pair0 + e;
         const int pos = pi < 22 ? pf : (pi < 43 ? ph : pw);
         const float2 cs = __ldg(rope_cs + pos * 64 + pi);
         // RMSNorm: bf16(x * rstd) then * weight, rounded to bf16 (model.py:83)
-        const float qa = bf16_round(bf16_round(bf16_lo(qw[e]) * q_rstd) * bf16_lo(gq[e]));
-        const float qb = bf16_round(bf16_round(bf16_hi(qw[e]) * q_rstd) * bf16_hi(gq[e]));
-        const float ka = bf16_round(bf16_round(bf16_lo(kw[e]) * k_rstd) * bf16_lo(gk[e]));
-        const float kb = bf16_round(bf16_round(bf16_hi(kw[e]) * k_rstd) * bf16_hi(gk[e]));
-        oq[e] = pack_bf16x2(qa * cs.x - qb * cs.y, qa * cs.y + qb * cs.x);
-        ok[e] = pack_bf16x2(ka * cs.x - kb * cs.y, ka * cs.y + kb * cs.x);
+        const float a = bf16_round(bf16_round(bf16_lo(xw[e]) * rstd) * bf16_lo(gw[e]));
+        const float b = bf16_round(bf16_round(bf16_hi(xw[e]) * rstd) * bf16_hi(gw[e]));
+        o[e] = pack_bf16x2(a * cs.x - b * cs.y, a * cs.y + b * cs.x);
       }
+      const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
       if (!sharded) {
-        qo[vi] = make_uint4(oq[0], oq[1], oq[2], oq[3]);
-        if (dst >= 0) {
-          ko[vi] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
-          vo[vi] = vv[i];
-        }
+        orow[vi] = ov;
       } else {
         // head exchange fused into the store: this 16-byte vector belongs to head vi/16, owned by
         // rank (vi/16)/heads_per_rank; write it straight into that rank's (peer-mapped) buffers
         const int r = vi / vec_per_rank, lv = vi - r * vec_per_rank;
-        const int64_t ldp = static_cast<int64_t>(vec_per_rank);  // peer leading dim in uint4 units
-        reinterpret_cast<uint4*>(sh.q_peers[r])[static_cast<int64_t>(grow) * ldp + lv] =
-            make_uint4(oq[0], oq[1], oq[2], oq[3]);
-        if (dst >= 0) {
-          reinterpret_cast<uint4*>(sh.k_peers[r])[static_cast<int64_t>(dst) * ldp + lv] =
-              make_uint4(ok[0], ok[1], ok[2], ok[3]);
-          reinterpret_cast<uint4*>(sh.v_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = vr[vi];
-        }
+        if (part == 0) reinterpret_cast<uint4*>(sh.q_peers[r])[static_cast<int64_t>(grow) * ldp + lv] = ov;
+        else reinterpret_cast<uint4*>(sh.k_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = ov;
       }
     }
   }
@@ -555,7 +551,9 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
                 "rmsnorm_rope_append: bad strides / grid");
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   auto kern = (C + 255) / 256 <= 6 ? rmsnorm_rope_append_kernel<6> : rmsnorm_rope_append_kernel<kMaxVec>;
-  LLB_CUDA(launch_ex(kern, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
+  // grid.y: q / k / v parts; without a cache (norm + rope only) and unsharded there is nothing to do for v
+  const int parts = (k_cache != nullptr || sh.n_ranks > 1) ? 3 : 1;
+  LLB_CUDA(launch_ex(kern, dim3(grid, parts), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<__nv_bfloat16*>(q_out), ldq,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), ld_cache, rows, C,
       static_cast<const __nv_bfloat16*>(wq), static_cast<const __nv_bfloat16*>(wk), eps,

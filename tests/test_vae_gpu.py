@@ -269,3 +269,26 @@ def test_full_size_decoder_first_frames_vs_oracle():
             err = rel_l2(a, b)
             print(f"full-size VAE frames {sl}: rel-L2 vs oracle (torch / cuDNN bf16) {err:.3e}")
             assert err < 3e-2   # two bf16 implementations of a 31-convolution stack; the reference's bf16-vs-fp32 is 1.7e-2
+
+
+def test_long_stream_has_no_ring_drift():
+    """40 latent frames streamed in uneven calls: every ring wraps many times; the error against the oracle
+    (same stream, same weights, on the GPU through torch ops) must stay at the two-bf16-implementations floor."""
+    from oracle import vae_oracle as vo
+    from oracle.make_vae_golden import SMALL, latents, scale_of
+    cfg = vo.VaeConfig(**SMALL)
+    sd = vo.init_state_dict(cfg, seed=8, dtype=torch.bfloat16)
+    dec = _decoder(SMALL, sd)
+    oracle = vo.VaeDecoderOracle(cfg, sd).to(DEV)
+    scale = [s.to(DEV) for s in scale_of(cfg, torch.bfloat16)]
+    z = latents(cfg, 60, 40).to(torch.bfloat16).to(DEV)
+    errs, pos = [], 0
+    with torch.no_grad():
+        for n in (1, 3, 3, 2, 5, 1, 1, 4, 3, 3, 7, 3, 4):
+            a = dec.cached_decode(z[:, :, pos:pos + n], scale)
+            b = oracle.cached_decode(z[:, :, pos:pos + n], scale).float().clamp_(-1, 1)
+            errs.append(rel_l2(a, b))
+            pos += n
+    assert pos == 40
+    print("per-call rel-L2:", " ".join(f"{e:.2e}" for e in errs))
+    assert max(errs) < 3e-2 and errs[-1] < 1.5 * (sum(errs[:4]) / 4)
