@@ -9,13 +9,20 @@
 // ring positions in_t0 .. in_t0 + T - 1 by the producing kernel and the taps at t - 1, t - 2 simply read the
 // positions before them (zero-initialised ring == zero padding at the start of a stream).
 //
-// Structure: the persistent tcgen05 GEMM of gemm_bf16.cu with a different A operand.  One CTA tile is an
-// 8 x 16 pixel patch of one frame (M = 128 rows) times BN output channels; the K loop runs over
-// (tap, 64-channel chunk); for each k-block the TMA producer loads the patch shifted by the tap with ONE 4-D
-// box (c, w, h, frame) - coordinates outside the image, negative ones included, are zero-filled by the TMA
-// unit, which is the spatial zero padding - and the matching [BN x 64] slice of the tap-major weight matrix.
-// The MMA warp and the 8 epilogue warps are the GEMM's; the epilogue maps tile rows back to pixels and adds
-// the residual (x + h of ResidualBlock, vae.py:220) after rounding conv + bias to bf16, as the reference does.
+// Structure: the persistent tcgen05 GEMM of gemm_bf16.cu with a different A operand.  One CTA tile is a
+// 16 (h) x 8 (w) pixel patch of one frame (M = 128 rows, row = h_local * 8 + w_local) times BN output channels;
+// the K loop runs over (dt, dw, channel chunk, dh).  The A operand of the three vertical taps dh = 0, 1, 2 is
+// ONE TMA box: the patch plus a one-pixel halo above and below, [18 h x 8 w pixels x CK channels], loaded once
+// per (dt, dw, chunk).  With rows ordered h-major, eight consecutive rows (one 128-byte-swizzle atom) are the
+// eight pixels of one image row, so the window of tap dh is the same shared-memory tile entered one atom
+// further down: its UMMA descriptor is base + dh * atom.  Coordinates outside the image (also negative) are
+// zero-filled by the TMA unit, which is the spatial zero padding.  The kernels are bound by the bytes an SM can
+// take in (64 B/clk), so loading the activations once per three taps is what buys speed:
+// 18.4 + 3 x 24 KB instead of 3 x (16 + 24) KB per (dt, dw, chunk) at BN = 192.
+// Weights come from a tap-major [Cout, taps*Cin] matrix, one [BN x CK] slice per (tap, chunk), in a second
+// shared-memory ring.  The MMA warp and the 8 epilogue warps are the GEMM's; the epilogue maps tile rows back to
+// pixels, adds the residual (x + h of ResidualBlock, vae.py:220) after rounding conv + bias to bf16 as the
+// reference does, and can emit the RMS_norm + SiLU of the result for the next convolution.
 #include <stdlib.h>
 
 #include "llb_common.cuh"
@@ -23,35 +30,37 @@
 
 namespace llb {
 
-constexpr int kConvTH = 8, kConvTW = 16;  // pixel patch = 128 GEMM rows
+constexpr int kConvTH = 16, kConvTW = 8;  // pixel patch = 128 GEMM rows, h-major
 constexpr int kConvEpiWarps = 8;
 constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
 constexpr int kConvEpiStageBytesPerWarp = 32 * 64;
+constexpr int kConvAStages = 3;
 
-// BN: output channels per tile (64 / 96 / 128 / 192).  CK: channels per k-block: 64 (128-byte swizzle rows) or
+// BN: output channels per tile (64 / 96 / 128 / 192).  CK: channels per chunk: 64 (128-byte swizzle rows) or
 // 32 (64-byte rows) - the latter for layers whose channel count is a multiple of 32 only (the 96-channel
-// full-resolution stage), so that no zero padding is moved or multiplied.
-// CPS: channel chunks per pipeline stage - with 32-channel chunks one k-block is only two short MMAs, too
-// little work per barrier round trip, so a stage then carries all three chunks of a 96-channel tap.
+// full-resolution stage), so that no zero padding is moved or multiplied.  CPS: chunks per pipeline stage -
+// with 32-channel chunks one chunk is only two short MMAs per tap, too little work per barrier round trip, so
+// a stage then carries all three chunks of the 96 channels.
 template <int BN, int CK, int CPS>
 struct ConvCfg {
-  static constexpr int kChunkA = 128 * CK * 2;
+  static constexpr int kAtomBytes = 8 * CK * 2;                       // 8 rows = one image row of the patch
+  static constexpr int kChunkA = (kConvTH + 2) * 8 * CK * 2;          // patch + halo rows: 144 x CK
   static constexpr int kChunkB = BN * CK * 2;
   static constexpr int kStageA = CPS * kChunkA;
   static constexpr int kStageB = CPS * kChunkB;
-  static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int kSlabs = BN / 32;                      // 32-column epilogue slabs, dealt out alternately
   static constexpr int kMySlabs = (kSlabs + 1) / 2;          // most slabs one epilogue warp handles
   static constexpr int kEpiVecBytesPerWarp = 2 * kMySlabs * 32 * 4;  // fp32 bias and norm gamma of its slabs
   static constexpr int kNormXchgBytes = 2 * 8 * 32 * 4;      // per-row sums of squares, double-buffered by tile parity
   static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp) + kNormXchgBytes;
-  static constexpr int kFixedBytes = 1024 + kEpiBytes + 256;
-  static constexpr int kStagesFit = (232448 - kFixedBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 12 ? 12 : kStagesFit;
-  static_assert(2 * kStages + 5 <= 32, "barrier block is 256 bytes");
-  static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
-  static_assert(kStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
+  static constexpr int kFixedBytes = 1024 + kEpiBytes + 256 + kConvAStages * kStageA;
+  static constexpr int kBFit = (232448 - kFixedBytes) / kStageB;
+  static constexpr int kBStages = kBFit > 10 ? 10 : kBFit;
+  static constexpr int kSmemBytes = kFixedBytes + kBStages * kStageB;
+  static_assert(kBStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
+  static_assert(2 * kConvAStages + 2 * kBStages + 5 <= 32, "barrier block is 256 bytes");
+  static_assert(kStageA % 1024 == 0 && kChunkB % 512 == 0, "swizzle atom alignment");
 };
 
 struct ConvParams {
@@ -81,37 +90,42 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
               const ConvParams p) {
   using Cfg = ConvCfg<BN, CK, CPS>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kBStages = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t stage_base = smem_base;
-  const uint32_t epi_base = smem_base + kStages * Cfg::kStageBytes;
-  uint8_t* epi_gen = smem_gen + kStages * Cfg::kStageBytes;
+  const uint32_t a_base = smem_base;                                    // kConvAStages halo tiles
+  const uint32_t b_base = a_base + kConvAStages * Cfg::kStageA;         // kBStages weight slices
+  const uint32_t epi_base = b_base + kBStages * Cfg::kStageB;
+  uint8_t* epi_gen = smem_gen + (epi_base - smem_base);
   const uint32_t bar_base = epi_base + Cfg::kEpiBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (kConvAStages + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kConvAStages + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (2 * kConvAStages + kBStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kConvAStages + 2 * kBStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kConvAStages + 2 * kBStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kConvAStages + 2 * kBStages + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::kEpiBytes + 8 * (2 * kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(epi_gen + Cfg::kEpiBytes + 8 * (2 * kConvAStages + 2 * kBStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_per_frame = p.tiles_h * p.tiles_w;
   const int num_m_tiles = p.T * tiles_per_frame;
   const int num_tiles = num_m_tiles * p.num_n_tiles;
-  const int cchunks = p.Cin / (CK * CPS);  // chunk groups (= pipeline stages) per tap
-  const int taps = p.kt * p.kh * p.kw;
-  const int num_kb = taps * cchunks;
+  const int cgroups = p.Cin / (CK * CPS);  // chunk groups per tap
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_in);
     tma_prefetch_desc(&tmap_w);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < kConvAStages; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -131,8 +145,10 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      // bytes of one halo box: (16 + kh - 1) image rows of 8 pixels
+      const uint32_t a_bytes = static_cast<uint32_t>(CPS) * (kConvTH + p.kh - 1) * 8 * CK * 2;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_idx = tile % num_m_tiles;
         const int n_idx = tile / num_m_tiles;
@@ -140,27 +156,28 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
         const int rem = m_idx - t * tiles_per_frame;
         const int h0 = (rem / p.tiles_w) * kConvTH;
         const int w0 = (rem % p.tiles_w) * kConvTW;
-        int kb = 0;
         for (int dt = 0; dt < p.kt; ++dt) {
           // causal: tap dt reads frame t + dt - (kt - 1) of the stream = ring slot before the new frames
           int tin = (p.in_t0 + t + dt - (p.kt - 1)) % p.in_frames;
           if (tin < 0) tin += p.in_frames;
-          for (int dh = 0; dh < p.kh; ++dh) {
-            for (int dw = 0; dw < p.kw; ++dw) {
-              const int tap = (dt * p.kh + dh) * p.kw + dw;
-              for (int cc = 0; cc < cchunks; ++cc, ++kb) {
-                mbar_wait(empty_bar(stage), phase ^ 1);
-                const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
-                const uint32_t sb = sa + Cfg::kStageA;
-                mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          for (int dw = 0; dw < p.kw; ++dw) {
+            for (int cg = 0; cg < cgroups; ++cg) {
+              mbar_wait(aempty_bar(as), aph ^ 1);
+              mbar_arrive_expect_tx(afull_bar(as), a_bytes);
 #pragma unroll
-                for (int j = 0; j < CPS; ++j) {
-                  const int c0 = (cc * CPS + j) * CK;
-                  tma_load_4d(sa + j * Cfg::kChunkA, &tmap_in, full_bar(stage), c0, w0 + dw - p.kw / 2,
-                              h0 + dh - p.kh / 2, tin);
-                  tma_load_2d(sb + j * Cfg::kChunkB, &tmap_w, full_bar(stage), tap * p.Cin + c0, n_idx * BN);
-                }
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              for (int j = 0; j < CPS; ++j)
+                tma_load_4d(a_base + as * Cfg::kStageA + j * Cfg::kChunkA, &tmap_in, afull_bar(as),
+                            (cg * CPS + j) * CK, w0 + dw - p.kw / 2, h0 - p.kh / 2, tin);
+              if (++as == kConvAStages) { as = 0; aph ^= 1; }
+              for (int dh = 0; dh < p.kh; ++dh) {
+                const int tap = (dt * p.kh + dh) * p.kw + dw;
+                mbar_wait(bempty_bar(bs), bph ^ 1);
+                mbar_arrive_expect_tx(bfull_bar(bs), Cfg::kStageB);
+#pragma unroll
+                for (int j = 0; j < CPS; ++j)
+                  tma_load_2d(b_base + bs * Cfg::kStageB + j * Cfg::kChunkB, &tmap_w, bfull_bar(bs),
+                              tap * p.Cin + (cg * CPS + j) * CK, n_idx * BN);
+                if (++bs == kBStages) { bs = 0; bph ^= 1; }
               }
             }
           }
@@ -170,34 +187,44 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
     int it = 0;
+    const int groups = p.kt * p.kw * cgroups;  // halo tiles per output tile
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kStageA;
-        const uint64_t da = CK == 64 ? umma_desc_kmajor(sa) : umma_desc_kmajor_sw64(sa);
-        const uint64_t db = CK == 64 ? umma_desc_kmajor(sb) : umma_desc_kmajor_sw64(sb);
-        if (elect_one()) {
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(afull_bar(as), aph);
+        const uint32_t sa = a_base + as * Cfg::kStageA;
+        for (int dh = 0; dh < p.kh; ++dh) {
+          mbar_wait(bfull_bar(bs), bph);
+          tc_fence_after();
+          const uint32_t sb = b_base + bs * Cfg::kStageB;
+          // the window of vertical tap dh starts dh image rows (= dh swizzle atoms) into the halo tile
+          const uint64_t da = CK == 64 ? umma_desc_kmajor(sa + dh * Cfg::kAtomBytes)
+                                       : umma_desc_kmajor_sw64(sa + dh * Cfg::kAtomBytes);
+          const uint64_t db = CK == 64 ? umma_desc_kmajor(sb) : umma_desc_kmajor_sw64(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < CPS; ++j)
+            for (int j = 0; j < CPS; ++j)
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k)
-              umma_ss(d_tmem, da + j * (Cfg::kChunkA >> 4) + 2 * k, db + j * (Cfg::kChunkB >> 4) + 2 * k, idesc,
-                      (kb | j | k) != 0);
-          umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+              for (int k = 0; k < CK / 16; ++k)
+                umma_ss(d_tmem, da + j * (Cfg::kChunkA >> 4) + 2 * k, db + j * (Cfg::kChunkB >> 4) + 2 * k, idesc,
+                        (g | dh | j | k) != 0);
+            umma_commit(bempty_bar(bs));
+            if (dh == p.kh - 1) {
+              umma_commit(aempty_bar(as));
+              if (g == groups - 1) umma_commit(tfull_bar(acc));
+            }
+          }
+          __syncwarp();
+          if (++bs == kBStages) { bs = 0; bph ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++as == kConvAStages) { as = 0; aph ^= 1; }
       }
     }
   } else {
@@ -238,8 +265,8 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       bool row_ok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int row = q * 32 + i * 8 + (lane >> 2);  // row of the 8 x 16 patch: h-major
-        const int ph = h0 + (row >> 4), pw = w0 + (row & 15);
+        const int row = q * 32 + i * 8 + (lane >> 2);  // row of the 16 x 8 patch: h-major
+        const int ph = h0 + (row >> 3), pw = w0 + (row & 7);
         row_ok[i] = ph < p.H && pw < p.W;
         pix[i] = static_cast<int64_t>(ph) * p.W + pw;
       }
@@ -455,7 +482,8 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   }
 
   CUtensorMap ti, tw;
-  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH, kConvTW, ck, 2 * ck);
+  // one box = the 16 x 8 patch plus its halo rows for the vertical taps
+  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH + d->kh - 1, kConvTW, ck, 2 * ck);
   if (rc) return rc;
   const int64_t kdim = static_cast<int64_t>(d->kt) * d->kh * d->kw * d->Cin;
   rc = make_tmap_2d_bf16_sw(&tw, d->weight, d->Cout, kdim, kdim, bn, ck, 2 * ck);
