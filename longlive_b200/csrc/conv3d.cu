@@ -34,32 +34,37 @@ constexpr int kConvTH = 16, kConvTW = 8;  // pixel patch = 128 GEMM rows, h-majo
 constexpr int kConvEpiWarps = 8;
 constexpr int kConvThreads = 64 + kConvEpiWarps * 32;
 constexpr int kConvEpiStageBytesPerWarp = 32 * 64;
-constexpr int kConvAStages = 3;
 
 // BN: output channels per tile (64 / 96 / 128 / 192).  CK: channels per chunk: 64 (128-byte swizzle rows) or
 // 32 (64-byte rows) - the latter for layers whose channel count is a multiple of 32 only (the 96-channel
 // full-resolution stage), so that no zero padding is moved or multiplied.  CPS: chunks per pipeline stage -
 // with 32-channel chunks one chunk is only two short MMAs per tap, too little work per barrier round trip, so
 // a stage then carries all three chunks of the 96 channels.
-template <int BN, int CK, int CPS>
+// MT: patches per CTA tile, stacked vertically (MT * 16 image rows in ONE halo box): each weight slice then
+// feeds MT MMAs, halving the weight bytes per flop where BN is small (two accumulators of BN <= 128 columns,
+// double-buffered, still fit the 512 TMEM columns).
+template <int BN, int CK, int CPS, int MT>
 struct ConvCfg {
+  static constexpr int kAStages = MT == 2 ? 2 : 3;
+  static constexpr int kPatchH = kConvTH * MT;
   static constexpr int kAtomBytes = 8 * CK * 2;                       // 8 rows = one image row of the patch
-  static constexpr int kChunkA = (kConvTH + 2) * 8 * CK * 2;          // patch + halo rows: 144 x CK
+  static constexpr int kChunkA = (kPatchH + 2) * 8 * CK * 2;          // patches + halo rows
   static constexpr int kChunkB = BN * CK * 2;
   static constexpr int kStageA = CPS * kChunkA;
   static constexpr int kStageB = CPS * kChunkB;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kTmemCols = (2 * MT * BN <= 128) ? 128 : (2 * MT * BN <= 256 ? 256 : 512);
+  static_assert(2 * MT * BN <= 512, "TMEM columns");
   static constexpr int kSlabs = BN / 32;                      // 32-column epilogue slabs, dealt out alternately
   static constexpr int kMySlabs = (kSlabs + 1) / 2;          // most slabs one epilogue warp handles
   static constexpr int kEpiVecBytesPerWarp = 2 * kMySlabs * 32 * 4;  // fp32 bias and norm gamma of its slabs
   static constexpr int kNormXchgBytes = 2 * 8 * 32 * 4;      // per-row sums of squares, double-buffered by tile parity
   static constexpr int kEpiBytes = kConvEpiWarps * (kConvEpiStageBytesPerWarp + kEpiVecBytesPerWarp) + kNormXchgBytes;
-  static constexpr int kFixedBytes = 1024 + kEpiBytes + 256 + kConvAStages * kStageA;
+  static constexpr int kFixedBytes = 1024 + kEpiBytes + 256 + kAStages * kStageA;
   static constexpr int kBFit = (232448 - kFixedBytes) / kStageB;
   static constexpr int kBStages = kBFit > 10 ? 10 : kBFit;
   static constexpr int kSmemBytes = kFixedBytes + kBStages * kStageB;
   static_assert(kBStages >= 3 && kSmemBytes <= 232448, "shared memory budget");
-  static_assert(2 * kConvAStages + 2 * kBStages + 5 <= 32, "barrier block is 256 bytes");
+  static_assert(2 * kAStages + 2 * kBStages + 5 <= 32, "barrier block is 256 bytes");
   static_assert(kStageA % 1024 == 0 && kChunkB % 512 == 0, "swizzle atom alignment");
 };
 
@@ -85,12 +90,13 @@ struct ConvParams {
 // the input of the NEXT convolution - so the normalisation costs no pass over HBM of its own.  The two
 // epilogue warps of a TMEM lane quadrant each see half of a pixel's channels; they exchange their partial
 // sums of squares through shared memory and a 64-thread named barrier.
-template <int BN, int CK, int CPS, bool kNorm>
+template <int BN, int CK, int CPS, bool kNorm, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
               const ConvParams p) {
-  using Cfg = ConvCfg<BN, CK, CPS>;
+  using Cfg = ConvCfg<BN, CK, CPS, MT>;
   constexpr int kBStages = Cfg::kBStages;
+  constexpr int kConvAStages = Cfg::kAStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -148,13 +154,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       // bytes of one halo box: (16 + kh - 1) image rows of 8 pixels
-      const uint32_t a_bytes = static_cast<uint32_t>(CPS) * (kConvTH + p.kh - 1) * 8 * CK * 2;
+      const uint32_t a_bytes = static_cast<uint32_t>(CPS) * (Cfg::kPatchH + p.kh - 1) * 8 * CK * 2;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_idx = tile % num_m_tiles;
         const int n_idx = tile / num_m_tiles;
         const int t = m_idx / tiles_per_frame;
         const int rem = m_idx - t * tiles_per_frame;
-        const int h0 = (rem / p.tiles_w) * kConvTH;
+        const int h0 = (rem / p.tiles_w) * Cfg::kPatchH;
         const int w0 = (rem % p.tiles_w) * kConvTW;
         for (int dt = 0; dt < p.kt; ++dt) {
           // causal: tap dt reads frame t + dt - (kt - 1) of the stream = ring slot before the new frames
@@ -196,7 +202,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * (MT * BN);
       for (int g = 0; g < groups; ++g) {
         mbar_wait(afull_bar(as), aph);
         const uint32_t sa = a_base + as * Cfg::kStageA;
@@ -210,11 +216,13 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
           const uint64_t db = CK == 64 ? umma_desc_kmajor(sb) : umma_desc_kmajor_sw64(sb);
           if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < CPS; ++j)
+            for (int mt = 0; mt < MT; ++mt)  // patch mt sits 16 image rows (16 atoms) further down the halo tile
 #pragma unroll
-              for (int k = 0; k < CK / 16; ++k)
-                umma_ss(d_tmem, da + j * (Cfg::kChunkA >> 4) + 2 * k, db + j * (Cfg::kChunkB >> 4) + 2 * k, idesc,
-                        (g | dh | j | k) != 0);
+              for (int j = 0; j < CPS; ++j)
+#pragma unroll
+                for (int k = 0; k < CK / 16; ++k)
+                  umma_ss(d_tmem + mt * BN, da + ((mt * kConvTH * Cfg::kAtomBytes + j * Cfg::kChunkA) >> 4) + 2 * k,
+                          db + j * (Cfg::kChunkB >> 4) + 2 * k, idesc, (g | dh | j | k) != 0);
             umma_commit(bempty_bar(bs));
             if (dh == p.kh - 1) {
               umma_commit(aempty_bar(as));
@@ -246,7 +254,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       const int n_idx = tile / num_m_tiles;
       const int t = m_idx / tiles_per_frame;
       const int rem = m_idx - t * tiles_per_frame;
-      const int h0 = (rem / p.tiles_w) * kConvTH;
+      const int h0 = (rem / p.tiles_w) * Cfg::kPatchH;
       const int w0 = (rem % p.tiles_w) * kConvTW;
       const int t_out = (p.out_t0 + t * p.out_t_step) % p.out_frames;
       const int t_res = has_res ? (p.res_t0 + t) % p.res_frames : 0;
@@ -260,21 +268,23 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
         if constexpr (kNorm) my_gamma[i * 32 + lane] = in ? __bfloat162float(p.norm_gamma[cg]) : 0.f;
       }
       __syncwarp();
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
       // pixel of each of the four rows this lane handles in the transposed (coalesced) phase
       int64_t pix[4];
       bool row_ok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = q * 32 + i * 8 + (lane >> 2);  // row of the 16 x 8 patch: h-major
-        const int ph = h0 + (row >> 3), pw = w0 + (row & 7);
+        const int ph = h0 + mt * kConvTH + (row >> 3), pw = w0 + (row & 7);
         row_ok[i] = ph < p.H && pw < p.W;
         pix[i] = static_cast<int64_t>(ph) * p.W + pw;
       }
       uint4 yfin[kNorm ? kMySlabs : 1][4];
       float ss[4] = {0.f, 0.f, 0.f, 0.f};
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN + h * 32;
 #pragma unroll
       for (int c = 0; c < kMySlabs; ++c) {
         if (2 * c + h >= Cfg::kSlabs) continue;  // warp-uniform
@@ -282,7 +292,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
         uint32_t v[32];
         tmem_ld32(t_row + c * 64, v);
         tmem_wait_ld();
-        if (2 * (c + 1) + h >= Cfg::kSlabs) {
+        if (2 * (c + 1) + h >= Cfg::kSlabs && mt == MT - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -343,8 +353,9 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
       }
       if constexpr (kNorm) {
         // sum of squares of each pixel over ALL its channels: the 4 lanes sharing a row, then the partner warp
-        float* mine = xchg + ((it & 1) * 8 + q * 2 + h) * 32;
-        const float* theirs = xchg + ((it & 1) * 8 + q * 2 + (h ^ 1)) * 32;
+        const int par = (it * MT + mt) & 1;
+        float* mine = xchg + (par * 8 + q * 2 + h) * 32;
+        const float* theirs = xchg + (par * 8 + q * 2 + (h ^ 1)) * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
@@ -388,6 +399,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
           }
         }
       }
+      }  // mt
     }
   }
 
@@ -399,12 +411,12 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
   }
 }
 
-template <int BN, int CK, int CPS, bool kNorm>
+template <int BN, int CK, int CPS, bool kNorm, int MT>
 static int launch_conv_n(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, CK, CPS>;
+  using Cfg = ConvCfg<BN, CK, CPS, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS, kNorm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS, kNorm, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -412,24 +424,30 @@ static int launch_conv_n(const CUtensorMap& ti, const CUtensorMap& tw, const Con
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.T * p.tiles_h * p.tiles_w * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  conv3d_kernel<BN, CK, CPS, kNorm><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
+  conv3d_kernel<BN, CK, CPS, kNorm, MT><<<grid, kConvThreads, Cfg::kSmemBytes, stream>>>(ti, tw, p);
   LLB_LAUNCH_CHECK("conv3d_kernel");
   return LLB_OK;
 }
 
 template <int BN, int CK, int CPS>
-static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-  return p.norm_out != nullptr ? launch_conv_n<BN, CK, CPS, true>(ti, tw, p, stream)
-                               : launch_conv_n<BN, CK, CPS, false>(ti, tw, p, stream);
+static int launch_conv(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, int mt, cudaStream_t stream) {
+  if constexpr (BN <= 128) {
+    if (mt == 2)
+      return p.norm_out != nullptr ? launch_conv_n<BN, CK, CPS, true, 2>(ti, tw, p, stream)
+                                   : launch_conv_n<BN, CK, CPS, false, 2>(ti, tw, p, stream);
+  }
+  return p.norm_out != nullptr ? launch_conv_n<BN, CK, CPS, true, 1>(ti, tw, p, stream)
+                               : launch_conv_n<BN, CK, CPS, false, 1>(ti, tw, p, stream);
 }
 
 template <int CK, int CPS>
-static int dispatch_conv(int bn, const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t s) {
+static int dispatch_conv(int bn, const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, int mt,
+                         cudaStream_t s) {
   switch (bn) {
-    case 192: return launch_conv<192, CK, CPS>(ti, tw, p, s);
-    case 128: return launch_conv<128, CK, CPS>(ti, tw, p, s);
-    case 96: return launch_conv<96, CK, CPS>(ti, tw, p, s);
-    default: return launch_conv<64, CK, CPS>(ti, tw, p, s);
+    case 192: return launch_conv<192, CK, CPS>(ti, tw, p, mt, s);
+    case 128: return launch_conv<128, CK, CPS>(ti, tw, p, mt, s);
+    case 96: return launch_conv<96, CK, CPS>(ti, tw, p, mt, s);
+    default: return launch_conv<64, CK, CPS>(ti, tw, p, mt, s);
   }
 }
 
@@ -466,7 +484,11 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
   p.res = static_cast<const __nv_bfloat16*>(d->res);
   p.res_frames = d->res_frames > 0 ? d->res_frames : 1; p.res_t0 = d->res_t0;
   p.bias = static_cast<const __nv_bfloat16*>(d->bias);
-  p.tiles_h = (d->H + kConvTH - 1) / kConvTH;
+  // two stacked patches per CTA when the accumulators fit (BN <= 128) and the image is tall enough to fill the SMs
+  const char* mt_env = getenv("LLB_CONV_MT");
+  int mt = (bn <= 128 && d->H >= 64) ? 2 : 1;
+  if (mt_env != nullptr && (mt_env[0] == '1' || (mt_env[0] == '2' && bn <= 128))) mt = mt_env[0] - '0';
+  p.tiles_h = (d->H + kConvTH * mt - 1) / (kConvTH * mt);
   p.tiles_w = (d->W + kConvTW - 1) / kConvTW;
   p.num_n_tiles = (d->Cout + bn - 1) / bn;
   p.norm_out = static_cast<__nv_bfloat16*>(d->norm_out);
@@ -483,12 +505,12 @@ extern "C" int llb_conv3d(const llb_conv3d_desc* d, void* stream) {
 
   CUtensorMap ti, tw;
   // one box = the 16 x 8 patch plus its halo rows for the vertical taps
-  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH + d->kh - 1, kConvTW, ck, 2 * ck);
+  int rc = make_tmap_4d_bf16(&ti, d->in, d->in_frames, d->H, d->W, d->ld_in, kConvTH * mt + d->kh - 1, kConvTW, ck, 2 * ck);
   if (rc) return rc;
   const int64_t kdim = static_cast<int64_t>(d->kt) * d->kh * d->kw * d->Cin;
   rc = make_tmap_2d_bf16_sw(&tw, d->weight, d->Cout, kdim, kdim, bn, ck, 2 * ck);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ck == 64) return dispatch_conv<64, 1>(bn, ti, tw, p, s);
-  return (d->Cin / 32) % 3 == 0 ? dispatch_conv<32, 3>(bn, ti, tw, p, s) : dispatch_conv<32, 1>(bn, ti, tw, p, s);
+  if (ck == 64) return dispatch_conv<64, 1>(bn, ti, tw, p, mt, s);
+  return (d->Cin / 32) % 3 == 0 ? dispatch_conv<32, 3>(bn, ti, tw, p, mt, s) : dispatch_conv<32, 1>(bn, ti, tw, p, mt, s);
 }

@@ -25,10 +25,12 @@ def _cl(x):  # [C, T, H, W] -> channels-last [T, H, W, C]
                                             (192, 64, (3, 1, 1), 9, 16), (64, 64, (1, 1, 1), 8, 16), (384, 384, (3, 3, 3), 12, 20),
                                             (96, 96, (3, 3, 3), 20, 36), (32, 96, (3, 3, 3), 9, 17), (192, 96, (1, 3, 3), 16, 32),
                                             (96, 32, (3, 3, 3), 11, 19)])
-def test_conv3d_matches_torch_with_ring_history(cin, cout, k, H, W):
+@pytest.mark.parametrize("mt", ["1", "2"])
+def test_conv3d_matches_torch_with_ring_history(monkeypatch, mt, cin, cout, k, H, W):
     """Two consecutive calls (T = 2 then T = 3) on a 5-frame ring: the second call's temporal taps must see the
     first call's last frames through the ring (wrap-around included), exactly like CausalConv3d with its cache."""
     from longlive_b200 import vae
+    monkeypatch.setenv("LLB_CONV_MT", mt)   # patches per CTA tile (2 is only honoured for <= 128 output channels)
     g = torch.Generator().manual_seed(cin + cout + H)
     kt, kh, kw = k
     w = (torch.randn(cout, cin, kt, kh, kw, generator=g) / (cin * kt * kh * kw) ** 0.5).to(torch.bfloat16)
@@ -167,13 +169,15 @@ def test_pipeline_decodes_with_native_vae_full_resolution():
 
 
 @pytest.mark.parametrize("cin,cout,silu", [(96, 96, True), (192, 192, True), (64, 32, False), (128, 128, True)])
-def test_conv3d_fused_norm_matches_separate_norm(cin, cout, silu):
+@pytest.mark.parametrize("mt", ["1", "2"])
+def test_conv3d_fused_norm_matches_separate_norm(monkeypatch, mt, cin, cout, silu):
     """llb_conv3d with the RMS_norm (+SiLU) of its result fused into the epilogue == llb_conv3d followed by
     llb_vae_norm, and both == torch (conv -> + residual -> normalize * sqrt(C) * gamma -> SiLU)."""
     from longlive_b200 import vae
     from oracle import vae_oracle as vo
+    monkeypatch.setenv("LLB_CONV_MT", mt)
     g = torch.Generator().manual_seed(cin * 3 + cout)
-    H, W, T = 13, 21, 2
+    H, W, T = 37, 21, 2
     cinp, coutp = (cin + 63) // 64 * 64, (cout + 63) // 64 * 64
     w = (torch.randn(cout, cin, 3, 3, 3, generator=g) / (27 * cin) ** 0.5).to(torch.bfloat16)
     b = (0.1 * torch.randn(cout, generator=g)).to(torch.bfloat16)
