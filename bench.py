@@ -136,7 +136,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_fwd * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs[1]: 21 latent frames 832x480, sink 3 + window 12 (bounded sample)",
-                       "model": "Wan2.1-T2V-1.3B shape, random init", "timed_on": "host CPU"},
+                       "shape": "Wan2.1-T2V-1.3B transformer shape, random init", "timed_on": "host CPU"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -320,7 +320,9 @@ def run_ours(args):
     steady = None
     if rank == 0:
         state["embeds"] = embeds_dev
-        pipe.inference(noise_dev, ["synthetic prompt"], profile=True)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):  # stdout carries the ONE JSON line only
+            pipe.inference(noise_dev, ["synthetic prompt"], profile=True)
         steady = pipe.last_profile
     roof = attention_roofline(torch, ops, dev) if rank == 0 else None
     if world > 1:
@@ -351,7 +353,7 @@ def run_ours(args):
         "config": {
             "workload": "configs[1]: 5 s single-prompt generation, 21 latent frames (7 chunks x 5 forwards) "
                         "at 832x480, frame sink 3 + local window 12, 4-step DMD, batch 1 per GPU",
-            "model": "Wan2.1-T2V-1.3B shape (30 blocks, dim 1536, 12x128 heads, FFN 8960), random init",
+            "shape": "Wan2.1-T2V-1.3B transformer shape (30 blocks, dim 1536, 12x128 heads, FFN 8960), random init",
             "parallelism": f"{world} independent stream(s), one per GPU, no data-path collective",
             "l2": "working set per step (2.8 GB weights + 3.5 GB KV ring) exceeds the 126 MB L2; no flush needed",
             "cuda_graph": bool(model.use_cuda_graph),
