@@ -144,6 +144,10 @@ int llb_peer_barrier(void* const* flags_peers_dev, int rank, int n_ranks, void* 
 #define LLB_EPI_BIAS_GATE_RES 3 /* res + y * gate[row / rows_per_gate]   (:456, :467-468)    */
 #define LLB_EPI_BIAS_RES 4      /* res + y                 (cross-attn residual, :460)       */
 #define LLB_EPI_BIAS_F32 5      /* y written as float32 (out is float*, ldo in floats): attention logits of the VAE decoder */
+#define LLB_EPI_BIAS_MUL 6      /* res * y: the gated FFN of the umT5 text encoder, fc1(x) * gelu(gate(x)) with
+                                   res = gelu(gate(x)) from a BIAS_GELU_BF16 launch (wan/modules/t5.py:133) */
+#define LLB_EPI_BIAS_GELU_BF16 7 /* the umT5 GELU module (wan/modules/t5.py:46-50): the tanh formula evaluated op by
+                                   op with a bf16 rounding after each, as the reference's tensor expression does */
 
 int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                   int M, int N, int K, int epilogue, const void* bias, const void* gate,
@@ -208,7 +212,8 @@ int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_out, int64_
                             int grid_h, int grid_w, const llb_step_params* p_dev,
                             const llb_qkv_shard* shard, void* stream);
 
-/* Plain WanRMSNorm over C channels: out = bf16(x * rsqrt(mean(x^2)+eps)) * w  (model.py:78-86). */
+/* Plain WanRMSNorm over C <= 8192 channels: out = bf16(x * rsqrt(mean(x^2)+eps)) * w  (model.py:78-86; also
+ * T5LayerNorm, t5.py:57-62). */
 int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
                 const void* w, float eps, void* stream);
 
@@ -282,6 +287,31 @@ int llb_vae_latent_in(const void* z, const void* mean, const void* inv_std, cons
                       void* out, int out_frames, int out_t0, int T, int zc, int64_t hw, int Cp, void* stream);
 /* decode_to_pixel epilogue (utils/wan_wrapper.py:112): [T, h*w, Cp] bf16 -> float [T, 3, h*w] clamped to [-1, 1] */
 int llb_vae_pixel_out(const void* in, float* out, int T, int64_t hw, int Cp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * umT5 text encoder kernels (reference wan/modules/t5.py, called from
+ * WanTextEncoder.forward, utils/wan_wrapper.py:43-57, in bf16 after `pipeline.to(dtype=torch.bfloat16)`,
+ * inference.py:134).  The block Linears run on llb_gemm_bf16 (no bias; the gated FFN uses BIAS_GELU followed
+ * by BIAS_MUL), T5LayerNorm on llb_rmsnorm (same arithmetic as WanRMSNorm; rows up to 8192 wide).
+ * Activations are [batch * rows_per_seq, C] bf16; rows_per_seq is the text length rounded as the caller
+ * likes (a multiple of 128) - rows >= the sequence's valid length are computed but never influence valid rows.
+ * ------------------------------------------------------------------------------------------ */
+/* nn.Embedding lookup (t5.py:288): out[b * rows_per_seq + r, :] = table[ids[b * ld_ids + r], :], ids int64 */
+int llb_embed_rows(const void* table, int64_t vocab, const void* ids, int64_t ld_ids, void* out, int64_t ldo,
+                   int batch, int rows_per_seq, int C, void* stream);
+/* T5Attention core (t5.py:96-111), head_dim 64, no 1/sqrt(d) scaling:
+ *   qkv [batch * rows_per_seq, ld_qkv] = q | k | v column blocks of width n_heads * 64 (fused projection output)
+ *   logits = bf16(bf16(q . k) + pos_emb[bucket_lut[key - query + lut_center]][head]); keys >= seq_lens[b] get
+ *   probability 0 (reference: finfo.min fill); out = bf16(softmax_fp32(logits) V) -> [batch * rows_per_seq, ldo].
+ *   pos_emb: the block's T5RelativeEmbedding table [num_buckets, n_heads] bf16 (t5.py:230-247);
+ *   bucket_lut: int32 [2 * lut_center + 1], host-evaluated _relative_position_bucket (t5.py:249-268). */
+int llb_t5_attn(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int batch, int rows_per_seq,
+                int n_heads, const int32_t* seq_lens_dev, const void* pos_emb, const int32_t* bucket_lut_dev,
+                int lut_center, void* stream);
+/* Final T5LayerNorm (t5.py:294) fused with WanTextEncoder's padding (`u[v:] = 0.0`, wan_wrapper.py:52-53):
+ *   out[b, r, :] = r < seq_lens[b] ? norm(x[b * rows_per_seq + r, :]) : 0   for r < rows_out */
+int llb_t5_final_norm(const void* x, int64_t ldx, void* out, int64_t ldo, int batch, int rows_per_seq,
+                      int rows_out, int C, const void* w, float eps, const int32_t* seq_lens_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 LLB_MAX_SEGS = 4
 
 # epilogues (include/llb200.h)
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_F32 = range(6)
+(EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_F32, EPI_BIAS_MUL,
+ EPI_BIAS_GELU_BF16) = range(8)
 
 
 class KvState(C.Structure):
@@ -180,6 +181,15 @@ _PROTOS = {
         [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
          C.c_int64, C.c_int, C.c_void_p]),
     "llb_vae_pixel_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "llb_embed_rows": (
+        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                  C.c_void_p]),
+    "llb_t5_attn": (
+        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_void_p]),
+    "llb_t5_final_norm": (
+        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                  C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -86,6 +86,18 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// The umT5 encoder's GELU module (wan/modules/t5.py:46-50) spells the tanh approximation out as seven bf16
+// tensor ops, each rounding its result; in particular 1 + tanh(u) cancels in bf16 for negative inputs.  Parity
+// with the reference means reproducing that chain, not the exact function.  x is already bf16-valued.
+__device__ __forceinline__ float gelu_bf16_chain_f(float x) {
+  const float p3 = bf16_round(x * x * x);                         // torch.pow(x, 3.0)
+  const float a = bf16_round(0.044715f * p3);
+  const float b = bf16_round(x + a);
+  const float c = bf16_round(0.7978845608028654f * b);            // math.sqrt(2 / pi) * (...)
+  const float t = bf16_round(1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * c)));  // tanh(c), error << bf16 ulp
+  const float u = bf16_round(1.0f + t);
+  return bf16_round(0.5f * x) * u;
+}
 
 // kFp8: A and W are e4m3 bytes (K-block = 128 elements = the same 128-byte swizzle row), the MMA is
 // kind::f8f6f4 (K = 32 per instruction, twice the bf16 rate) and the epilogue applies
@@ -245,7 +257,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     float* my_ws = my_bias + BN / 2;
     const uint32_t tempty_lead0 = kPair ? mapa_shared(tempty_bar(0), 0) : tempty_bar(0);
     const int epi = p.epilogue;
-    const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES);
+    const bool has_mul = epi == LLB_EPI_BIAS_MUL;
+    const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES || has_mul);
     const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
@@ -339,6 +352,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
             } else if (epi == LLB_EPI_BIAS_SILU) {
               y0 = silu_f(bf16_round(y0));
               y1 = silu_f(bf16_round(y1));
+            } else if (epi == LLB_EPI_BIAS_GELU_BF16) {
+              y0 = gelu_bf16_chain_f(bf16_round(y0));
+              y1 = gelu_bf16_chain_f(bf16_round(y1));
             }
             packed[e] = pack_bf16x2(y0, y1);
           }
@@ -386,7 +402,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   y0 = bf16_round(y0 * bf16_lo(gg[e]));
                   y1 = bf16_round(y1 * bf16_hi(gg[e]));
                 }
-                o[e] = pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
+                o[e] = has_mul ? pack_bf16x2(bf16_lo(xx[e]) * y0, bf16_hi(xx[e]) * y1)
+                               : pack_bf16x2(bf16_lo(xx[e]) + y0, bf16_hi(xx[e]) + y1);
               }
               y = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -460,13 +477,14 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
                 "gemm: leading dims must be 16-byte multiples");
   LLB_CHECK_ARG(!fp8 || (a_scale && w_scale && (reinterpret_cast<uintptr_t>(w_scale) & 15) == 0),
                 "gemm_fp8: needs a_scale[M] and a 16-byte aligned w_scale[N]");
-  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_F32, "gemm: unknown epilogue %d", epilogue);
+  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_GELU_BF16, "gemm: unknown epilogue %d", epilogue);
   LLB_CHECK_ARG(epilogue != LLB_EPI_BIAS_F32 || ldo % 4 == 0, "gemm: fp32 output needs ldo %% 4 == 0");
   if (epilogue == LLB_EPI_BIAS_GATE_RES) {
     LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
                   "gemm: gate/residual epilogue needs gate, res, rows_per_gate");
   }
-  if (epilogue == LLB_EPI_BIAS_RES) LLB_CHECK_ARG(res && ld_res % 8 == 0, "gemm: residual epilogue needs res");
+  if (epilogue == LLB_EPI_BIAS_RES || epilogue == LLB_EPI_BIAS_MUL)
+    LLB_CHECK_ARG(res && ld_res % 8 == 0, "gemm: residual / multiplier epilogue needs res");
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out must be 16-byte aligned");
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(res) & 15) == 0, "gemm: bias/gate/res must be 16-byte aligned");

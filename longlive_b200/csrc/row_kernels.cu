@@ -228,6 +228,59 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* 
   }
 }
 
+// Rows wider than one warp's register budget (C > 2048: T5LayerNorm of the umT5 text encoder, t5.py:57-62,
+// the same arithmetic as WanRMSNorm): one CTA of 256 threads per row, up to four 16-byte vectors per thread.
+constexpr int kWideThreads = 256;
+constexpr int kWideVec = 4;  // C <= 256 * 4 * 8 = 8192
+__global__ void __launch_bounds__(kWideThreads)
+rmsnorm_wide_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+                    int64_t ldo, int C, const __nv_bfloat16* __restrict__ wgt, float eps) {
+  __shared__ float red[kWideThreads / 32];
+  griddep_wait();
+  griddep_launch_dependents();
+  const int row = blockIdx.x;
+  const int nvec = C / 8;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx);
+  uint4 v[kWideVec];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kWideVec; ++i) {
+    const int vi = threadIdx.x + i * kWideThreads;
+    if (vi < nvec) {
+      v[i] = xr[vi];
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = bf16_lo(w[e]), b = bf16_hi(w[e]);
+        ss += a * a + b * b;
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kWideThreads / 32; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / static_cast<float>(C) + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo);
+#pragma unroll
+  for (int i = 0; i < kWideVec; ++i) {
+    const int vi = threadIdx.x + i * kWideThreads;
+    if (vi < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(wgt) + vi);
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(&g4);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = pack_bf16x2(bf16_round(bf16_lo(w[e]) * rstd) * bf16_lo(g[e]),
+                           bf16_round(bf16_hi(w[e]) * rstd) * bf16_hi(g[e]));
+      orow[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fused q/k RMSNorm + 3-D RoPE + KV-ring append.
 //   q  = rope(rmsnorm(qkv[:, 0:C]))        -> q_out                    (causal_model.py:122-128, 208-211)
@@ -515,8 +568,15 @@ extern "C" int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_
 extern "C" int llb_rmsnorm(const void* x, int64_t ldx, void* out, int64_t ldo, int rows, int C,
                            const void* w, float eps, void* stream) {
   LLB_CHECK_ARG(x && out && w && rows > 0, "rmsnorm: null tensor / no rows");
-  LLB_CHECK_ARG(C % 8 == 0 && C <= 32 * kMaxVec * 8, "rmsnorm: C=%d unsupported", C);
+  LLB_CHECK_ARG(C % 8 == 0 && C <= kWideThreads * kWideVec * 8, "rmsnorm: C=%d unsupported", C);
   LLB_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0, "rmsnorm: leading dims % 8");
+  if (C > 32 * kMaxVec * 8) {
+    LLB_CUDA(launch_ex(rmsnorm_wide_kernel, dim3(rows), dim3(kWideThreads), 0, static_cast<cudaStream_t>(stream), 1,
+        true, static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, C,
+        static_cast<const __nv_bfloat16*>(w), eps));
+    LLB_LAUNCH_CHECK("rmsnorm_wide_kernel");
+    return LLB_OK;
+  }
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   LLB_CUDA(launch_ex(rmsnorm_kernel, dim3(grid), dim3(kRowWarps * 32), 0, static_cast<cudaStream_t>(stream), 1, true,
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(out), ldo, rows, C,

@@ -12,14 +12,15 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_RES, EPI_BIAS_SILU,
-                   STEP_PARAMS_INT32, StepParams)
+from ._lib import (EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_BF16, EPI_BIAS_MUL,
+                   EPI_BIAS_RES, EPI_BIAS_SILU, STEP_PARAMS_INT32, StepParams)
 
 __all__ = [
     "gemm", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
     "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
     "build_rope_table", "launch_count",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES", "EPI_BIAS_F32",
+    "EPI_BIAS_MUL", "EPI_BIAS_GELU_BF16", "embed_rows", "t5_attention", "t5_final_norm",
 ]
 
 
@@ -341,3 +342,55 @@ def build_rope_table(head_dim: int = 128, max_pos: int = 1024, theta: float = 10
     ang = torch.cat(cols, dim=1)  # [max_pos, d/2]
     assert ang.shape[1] == d // 2
     return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# umT5 text encoder kernels (include/llb200.h, last section)
+def embed_rows(table: torch.Tensor, ids: torch.Tensor, rows_per_seq: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b * rows_per_seq + r] = table[ids[b, r]] for r < rows_per_seq; ids int64 [B, >= rows_per_seq]."""
+    _req(table, "table"); _req(ids, "ids", torch.int64)
+    B = ids.shape[0]
+    assert ids.shape[1] >= rows_per_seq
+    Cc = table.shape[1]
+    if out is None:
+        out = torch.empty((B * rows_per_seq, Cc), dtype=torch.bfloat16, device=table.device)
+    _req(out, "out")
+    rc = _lib.lib().llb_embed_rows(table.data_ptr(), table.shape[0], ids.data_ptr(), ids.stride(0), out.data_ptr(),
+                                   out.stride(0), B, rows_per_seq, Cc, _stream())
+    _lib.check(rc, "llb_embed_rows")
+    return out
+
+
+def t5_attention(qkv: torch.Tensor, batch: int, n_heads: int, seq_lens: torch.Tensor, pos_emb: torch.Tensor,
+                 bucket_lut: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T5Attention core on the fused projection output qkv [batch * rows_per_seq, 3 * n_heads * 64];
+    seq_lens int32 [batch] (device), pos_emb bf16 [num_buckets, n_heads], bucket_lut int32 [2 * center + 1]."""
+    _req(qkv, "qkv"); _req(pos_emb, "pos_emb"); _req(seq_lens, "seq_lens", torch.int32)
+    _req(bucket_lut, "bucket_lut", torch.int32)
+    rows = qkv.shape[0]
+    assert rows % batch == 0 and pos_emb.shape[1] == n_heads and pos_emb.is_contiguous()
+    if out is None:
+        out = torch.empty((rows, n_heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    _req(out, "out")
+    rc = _lib.lib().llb_t5_attn(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), batch, rows // batch,
+                                n_heads, seq_lens.data_ptr(), pos_emb.data_ptr(), bucket_lut.data_ptr(),
+                                (bucket_lut.numel() - 1) // 2, _stream())
+    _lib.check(rc, "llb_t5_attn")
+    return out
+
+
+def t5_final_norm(x: torch.Tensor, w: torch.Tensor, batch: int, rows_out: int, seq_lens: torch.Tensor,
+                  eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[batch, rows_out, C]: final T5LayerNorm of the valid rows, zeros elsewhere."""
+    _req(x, "x"); _req(w, "w"); _req(seq_lens, "seq_lens", torch.int32)
+    rows, Cc = x.shape
+    assert rows % batch == 0
+    if out is None:
+        out = torch.empty((batch, rows_out, Cc), dtype=torch.bfloat16, device=x.device)
+    _req(out, "out")
+    assert out.is_contiguous()
+    rc = _lib.lib().llb_t5_final_norm(x.data_ptr(), x.stride(0), out.data_ptr(), Cc, batch, rows // batch, rows_out,
+                                      Cc, w.data_ptr(), C.c_float(eps), seq_lens.data_ptr(), _stream())
+    _lib.check(rc, "llb_t5_final_norm")
+    return out
