@@ -204,6 +204,33 @@ def vae_decode_sample(torch, dev):
                     "Wan2.1 VAE decoder shape, random init; reference: 22 s / 240 latent frames on H100 (reports.md:37)"}
 
 
+def text_encoder_sample(torch, dev):
+    """Row before the path, reported beside the headline, never folded into it: one prompt
+    through the umT5 text encoder (umt5-xxl shape, random init, bf16) on libllb200 - token ids on the host in,
+    prompt_embeds [1, 512, 4096] on the device out."""
+    from longlive_b200 import synth
+    from longlive_b200.text_encoder import HashTokenizer, UMT5Encoder, WanTextEncoder
+    enc = UMT5Encoder(device=dev, dtype=torch.bfloat16)
+    synth.random_init_t5_(enc, seed=0)
+    te = WanTextEncoder(text_encoder=enc, tokenizer=HashTokenizer(seq_len=512))
+    prompt = " ".join(f"word{i}" for i in range(199))  # 200 tokens with </s>: a typical LongLive prompt length
+    te([prompt]); te([prompt])
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    st.record()
+    for _ in range(5):
+        out = te([prompt])["prompt_embeds"]
+    en.record()
+    torch.cuda.synchronize()
+    ms = st.elapsed_time(en) / 5
+    del te, enc
+    torch.cuda.empty_cache()
+    return {"ms_per_prompt": ms, "tokens": 200, "rows_computed": 256, "launches_per_prompt": 194,
+            "what": "WanTextEncoder.forward (synthetic tokenizer + umt5-xxl encoder, 24 blocks, dim 4096, bf16, random "
+                    "init) for one 200-token prompt; the reference's op sequence in eager PyTorch on the same GPU: "
+                    "20.8 ms (tools/t5_bench.py, profiles/r01_t5_bench.json)"}
+
+
 def attention_roofline(torch, ops, dev, iters=60):
     """Dominant kernel: self-attention at the steady-state shape, timed live with CUDA events on the
     launching stream, rotating over 4 K/V sets (460 MB > L2) like consecutive layers do."""
@@ -337,6 +364,12 @@ def run_ours(args):
             vae = vae_decode_sample(torch, dev)
         except Exception as e:  # informational: never fails the headline
             vae = {"error": str(e)[:200]}
+    text = None
+    if world == 1:
+        try:
+            text = text_encoder_sample(torch, dev)
+        except Exception as e:  # informational: never fails the headline
+            text = {"error": str(e)[:200]}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -370,6 +403,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "vae_decode": vae,
+        "text_encoder": text,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

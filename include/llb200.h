@@ -304,10 +304,12 @@ int llb_embed_rows(const void* table, int64_t vocab, const void* ids, int64_t ld
  *   logits = bf16(bf16(q . k) + pos_emb[bucket_lut[key - query + lut_center]][head]); keys >= seq_lens[b] get
  *   probability 0 (reference: finfo.min fill); out = bf16(softmax_fp32(logits) V) -> [batch * rows_per_seq, ldo].
  *   pos_emb: the block's T5RelativeEmbedding table [num_buckets, n_heads] bf16 (t5.py:230-247);
- *   bucket_lut: int32 [2 * lut_center + 1], host-evaluated _relative_position_bucket (t5.py:249-268). */
+ *   bucket_lut: int32 [2 * lut_center + 1], host-evaluated _relative_position_bucket (t5.py:249-268);
+ *   max_seq_len: host-known upper bound of seq_lens (sizes the shared-memory key / value stage; <= 0 means
+ *   rows_per_seq); lengths above it are clamped. */
 int llb_t5_attn(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int batch, int rows_per_seq,
-                int n_heads, const int32_t* seq_lens_dev, const void* pos_emb, const int32_t* bucket_lut_dev,
-                int lut_center, void* stream);
+                int n_heads, int max_seq_len, const int32_t* seq_lens_dev, const void* pos_emb,
+                const int32_t* bucket_lut_dev, int lut_center, void* stream);
 /* Final T5LayerNorm (t5.py:294) fused with WanTextEncoder's padding (`u[v:] = 0.0`, wan_wrapper.py:52-53):
  *   out[b, r, :] = r < seq_lens[b] ? norm(x[b * rows_per_seq + r, :]) : 0   for r < rows_out */
 int llb_t5_final_norm(const void* x, int64_t ldx, void* out, int64_t ldo, int batch, int rows_per_seq,

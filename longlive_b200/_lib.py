@@ -185,8 +185,8 @@ _PROTOS = {
         C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                   C.c_void_p]),
     "llb_t5_attn": (
-        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                  C.c_void_p, C.c_int, C.c_void_p]),
+        C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "llb_t5_final_norm": (
         C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                   C.c_float, C.c_void_p, C.c_void_p]),

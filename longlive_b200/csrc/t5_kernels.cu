@@ -108,9 +108,7 @@ t5_final_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bflo
 // so the rounding points are the reference's (an online softmax would round un-normalised probabilities).
 // ------------------------------------------------------------------------------------------------
 constexpr int kT5D = 64;
-constexpr int kT5Rows = 128;
 constexpr int kT5Stride = 72;
-constexpr int kT5Threads = 256;
 
 struct T5AttnParams {
   const __nv_bfloat16* qkv;  // [batch * rows_per_seq, ld]: q | k | v column blocks of width n_heads * 64
@@ -118,6 +116,7 @@ struct T5AttnParams {
   __nv_bfloat16* out;        // [batch * rows_per_seq, ldo]
   int64_t ldo;
   int rows_per_seq, n_heads;
+  int kv_cap;                     // shared-memory capacity in keys (multiple of 64, >= every valid length)
   const int32_t* seq_lens;        // [batch] valid keys per sequence
   const __nv_bfloat16* pos_emb;   // [num_buckets, n_heads]
   const int32_t* bucket_lut;      // [2 * lut_center + 1]: bucket of (key - query) + lut_center
@@ -136,40 +135,58 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& r0, 
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(saddr));
 }
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16(a) + bf16(b) -> bf16, two lanes at once (add.rn.bf16x2: one rounding of the exact sum, which is what the
+// reference's bf16 tensor add yields)
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 
-__global__ void __launch_bounds__(kT5Threads)
+// kWarps x 16 query rows per CTA (8 warps = 128 rows, or 16 warps = 256 rows when that still fills the GPU:
+// the keys / values of the head are then staged once per 256 rows and a 512-token prompt is a single wave).
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32)
 t5_attn_kernel(const T5AttnParams p) {
+  constexpr int kThreads = kWarps * 32, kRows = kWarps * 16;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int Lp = p.rows_per_seq;
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* Vs = Ks + static_cast<size_t>(Lp) * kT5Stride;
-  float* sbias = reinterpret_cast<float*>(Vs + static_cast<size_t>(Lp) * kT5Stride);  // [2 * Lp - 1]
+  __nv_bfloat16* Vs = Ks + static_cast<size_t>(p.kv_cap) * kT5Stride;
+  // bias2[i] = (bias[i], bias[i + 1]) as bf16x2 for offset index i = key - query + Lp - 1: one aligned 32-bit
+  // read serves the two adjacent keys of an accumulator pair whatever the parity of i
+  uint32_t* bias2 = reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(p.kv_cap) * kT5Stride);  // [2 * Lp - 1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
   const int width = p.n_heads * kT5D;
   const int64_t seq_row0 = static_cast<int64_t>(b) * Lp;
-  const int row_cta = blockIdx.x * kT5Rows;
+  const int row_cta = blockIdx.x * kRows;
   const int row_w = row_cta + warp * 16;  // first query row of this warp (within the sequence)
 
   int kv_len = p.seq_lens[b];
-  kv_len = kv_len < 0 ? 0 : (kv_len > Lp ? Lp : kv_len);
-  const int kv_pad = (kv_len + 63) & ~63;  // <= Lp because Lp % 128 == 0
+  kv_len = kv_len < 0 ? 0 : (kv_len > p.kv_cap ? p.kv_cap : kv_len);
+  const int kv_pad = (kv_len + 63) & ~63;  // <= kv_cap (a multiple of 64)
 
   if (kv_len == 0) {  // nothing to attend: the reference would produce a uniform average; rows are zeroed later anyway
-    for (int i = tid; i < kT5Rows * (kT5D / 8); i += kT5Threads) {
+    for (int i = tid; i < kRows * (kT5D / 8); i += kThreads) {
       const int r = i / (kT5D / 8), c = i % (kT5D / 8);
       *reinterpret_cast<uint4*>(p.out + (seq_row0 + row_cta + r) * p.ldo + h * kT5D + c * 8) = make_uint4(0, 0, 0, 0);
     }
     return;
   }
 
-  // ---- stage K, V (values of masked keys zeroed: 0 * garbage must stay 0) and this head's bias row
+  // ---- stage K, V (rows of masked keys zeroed: 0 * garbage must stay 0) and this head's bias pairs
   {
     const __nv_bfloat16* kbase = p.qkv + seq_row0 * p.ld + width + h * kT5D;
     const __nv_bfloat16* vbase = kbase + width;
-    for (int i = tid; i < kv_pad * (kT5D / 8); i += kT5Threads) {
+    for (int i = tid; i < kv_pad * (kT5D / 8); i += kThreads) {
       const int key = i >> 3, c = i & 7;
       uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
       if (key < kv_len) {
@@ -179,9 +196,12 @@ t5_attn_kernel(const T5AttnParams p) {
       *reinterpret_cast<uint4*>(Ks + key * kT5Stride + c * 8) = kk;
       *reinterpret_cast<uint4*>(Vs + key * kT5Stride + c * 8) = vv;
     }
-    for (int i = tid; i < 2 * Lp - 1; i += kT5Threads) {
-      const int bucket = p.bucket_lut[i - (Lp - 1) + p.lut_center];
-      sbias[i] = __bfloat162float(p.pos_emb[bucket * p.n_heads + h]);
+    const unsigned short* emb = reinterpret_cast<const unsigned short*>(p.pos_emb);
+    for (int i = tid; i < 2 * Lp - 1; i += kThreads) {
+      const int d = i - (Lp - 1) + p.lut_center;
+      const uint32_t lo = emb[p.bucket_lut[d] * p.n_heads + h];
+      const uint32_t hi = i + 1 < 2 * Lp - 1 ? emb[p.bucket_lut[d + 1] * p.n_heads + h] : 0u;
+      bias2[i] = lo | (hi << 16);
     }
   }
 
@@ -201,7 +221,10 @@ t5_attn_kernel(const T5AttnParams p) {
   __syncthreads();
 
   constexpr float kLog2e = 1.4426950408889634f;
-  // S block (16 query rows x 64 keys per warp) with bias, mask and the reference's two bf16 roundings
+  // S block (16 query rows x 64 keys per warp): bf16(bf16(q . k) + bias) as two packed roundings, keys beyond the
+  // prompt's length set to -inf (only the block that straddles kv_len needs the comparison)
+  const uint32_t* bias_r0 = bias2 + (2 * t - (row_w + g) + Lp - 1);  // + key column base; row g
+  const uint32_t* bias_r1 = bias_r0 - 8;                              // row g + 8
   auto logits_block = [&](int kb, float (&s)[8][4]) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -213,12 +236,17 @@ t5_attn_kernel(const T5AttnParams p) {
         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kc * 16 + 8);
         mma_bf16_16816(s[nt], qa[kc], b0, b1);
       }
+      const uint32_t x0 = add_bf16x2(pack_bf16x2(s[nt][0], s[nt][1]), bias_r0[kb + nt * 8]);
+      const uint32_t x1 = add_bf16x2(pack_bf16x2(s[nt][2], s[nt][3]), bias_r1[kb + nt * 8]);
+      s[nt][0] = bf16_lo(x0); s[nt][1] = bf16_hi(x0);
+      s[nt][2] = bf16_lo(x1); s[nt][3] = bf16_hi(x1);
+    }
+    if (kb + 64 > kv_len) {  // warp-uniform
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kb + nt * 8 + 2 * t + (e & 1);
-        const int row = row_w + g + (e >> 1) * 8;
-        const float x = bf16_round(bf16_round(s[nt][e]) + sbias[col - row + Lp - 1]);
-        s[nt][e] = col < kv_len ? x : -CUDART_INF_F;
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = kb + nt * 8 + 2 * t;
+        if (col >= kv_len) s[nt][0] = s[nt][2] = -CUDART_INF_F;
+        if (col + 1 >= kv_len) s[nt][1] = s[nt][3] = -CUDART_INF_F;
       }
     }
   };
@@ -235,18 +263,20 @@ t5_attn_kernel(const T5AttnParams p) {
       mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
       mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
+    float mneg[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);  // finite from the first block on (key 0 is never masked)
-      l_run[r] *= exp2f((m_run[r] - m_new) * kLog2e);
+      l_run[r] *= ex2_ftz((m_run[r] - m_new) * kLog2e);
       m_run[r] = m_new;
+      mneg[r] = -m_new * kLog2e;
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      l_run[0] += exp2f((s[nt][0] - m_run[0]) * kLog2e) + exp2f((s[nt][1] - m_run[0]) * kLog2e);
-      l_run[1] += exp2f((s[nt][2] - m_run[1]) * kLog2e) + exp2f((s[nt][3] - m_run[1]) * kLog2e);
+      l_run[0] += ex2_ftz(fmaf(s[nt][0], kLog2e, mneg[0])) + ex2_ftz(fmaf(s[nt][1], kLog2e, mneg[0]));
+      l_run[1] += ex2_ftz(fmaf(s[nt][2], kLog2e, mneg[1])) + ex2_ftz(fmaf(s[nt][3], kLog2e, mneg[1]));
     }
   }
 #pragma unroll
@@ -255,6 +285,7 @@ t5_attn_kernel(const T5AttnParams p) {
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
   }
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+  const float mneg0 = -m_run[0] * kLog2e, mneg1 = -m_run[1] * kLog2e;
 
   // ---- pass 2: P = bf16(softmax) exactly as the reference materialises it (.type_as(attn)), O += P V
   float o[8][4];
@@ -269,8 +300,8 @@ t5_attn_kernel(const T5AttnParams p) {
     uint32_t pa[4][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = exp2f((s[nt][0] - m_run[0]) * kLog2e) * inv0, p1 = exp2f((s[nt][1] - m_run[0]) * kLog2e) * inv0;
-      const float p2 = exp2f((s[nt][2] - m_run[1]) * kLog2e) * inv1, p3 = exp2f((s[nt][3] - m_run[1]) * kLog2e) * inv1;
+      const float p0 = ex2_ftz(fmaf(s[nt][0], kLog2e, mneg0)) * inv0, p1 = ex2_ftz(fmaf(s[nt][1], kLog2e, mneg0)) * inv0;
+      const float p2 = ex2_ftz(fmaf(s[nt][2], kLog2e, mneg1)) * inv1, p3 = ex2_ftz(fmaf(s[nt][3], kLog2e, mneg1)) * inv1;
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
     }
@@ -327,33 +358,42 @@ extern "C" int llb_t5_final_norm(const void* x, int64_t ldx, void* out, int64_t 
 }
 
 extern "C" int llb_t5_attn(const void* qkv, int64_t ld_qkv, void* out, int64_t ldo, int batch, int rows_per_seq,
-                           int n_heads, const int32_t* seq_lens_dev, const void* pos_emb,
+                           int n_heads, int max_seq_len, const int32_t* seq_lens_dev, const void* pos_emb,
                            const int32_t* bucket_lut_dev, int lut_center, void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(qkv && out && seq_lens_dev && pos_emb && bucket_lut_dev && batch > 0 && n_heads > 0,
                 "t5_attn: null tensor / bad shape");
-  LLB_CHECK_ARG(rows_per_seq > 0 && rows_per_seq % kT5Rows == 0 && rows_per_seq <= 1024,
-                "t5_attn: rows_per_seq=%d must be a multiple of %d (<= 1024)", rows_per_seq, kT5Rows);
+  LLB_CHECK_ARG(rows_per_seq > 0 && rows_per_seq % 128 == 0 && rows_per_seq <= 1024,
+                "t5_attn: rows_per_seq=%d must be a multiple of 128 (<= 1024)", rows_per_seq);
   LLB_CHECK_ARG(lut_center >= rows_per_seq - 1, "t5_attn: bucket LUT too short for %d rows", rows_per_seq);
   LLB_CHECK_ARG(ld_qkv % 8 == 0 && ldo % 8 == 0 && ld_qkv >= 3 * n_heads * kT5D && ldo >= n_heads * kT5D,
                 "t5_attn: leading dimensions");
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "t5_attn: 16-byte alignment");
-  const size_t smem = static_cast<size_t>(rows_per_seq) * kT5Stride * 2 * 2 + (2 * rows_per_seq - 1) * sizeof(float);
-  LLB_CHECK_ARG(smem <= 227 * 1024, "t5_attn: %d keys do not fit shared memory", rows_per_seq);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    LLB_CUDA(cudaFuncSetAttribute(t5_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
+  // shared memory holds the valid keys only (max_seq_len: host-known upper bound of seq_lens, <= 0 = rows_per_seq)
+  int kv_cap = max_seq_len > 0 && max_seq_len < rows_per_seq ? max_seq_len : rows_per_seq;
+  kv_cap = (kv_cap + 63) & ~63;
+  const size_t smem = static_cast<size_t>(kv_cap) * kT5Stride * 2 * 2 + (2 * rows_per_seq - 1) * sizeof(uint32_t);
+  LLB_CHECK_ARG(smem <= 227 * 1024, "t5_attn: %d keys do not fit shared memory", kv_cap);
+  // 256-row CTAs when they still cover most of the GPU in one wave, else 128-row CTAs
+  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
+  const bool wide = rows_per_seq % 256 == 0 && (rows_per_seq / 256) * n_heads * batch >= (sms * 3) / 4;
+  static size_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[wide]) {
+    if (wide) LLB_CUDA(cudaFuncSetAttribute(t5_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    else LLB_CUDA(cudaFuncSetAttribute(t5_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem[wide] = smem;
   }
   T5AttnParams p;
   p.qkv = static_cast<const __nv_bfloat16*>(qkv); p.ld = ld_qkv;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
-  p.rows_per_seq = rows_per_seq; p.n_heads = n_heads;
+  p.rows_per_seq = rows_per_seq; p.n_heads = n_heads; p.kv_cap = kv_cap;
   p.seq_lens = seq_lens_dev;
   p.pos_emb = static_cast<const __nv_bfloat16*>(pos_emb);
   p.bucket_lut = bucket_lut_dev; p.lut_center = lut_center;
-  t5_attn_kernel<<<dim3(rows_per_seq / kT5Rows, n_heads, batch), kT5Threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wide) t5_attn_kernel<16><<<dim3(rows_per_seq / 256, n_heads, batch), 512, smem, st>>>(p);
+  else t5_attn_kernel<8><<<dim3(rows_per_seq / 128, n_heads, batch), 256, smem, st>>>(p);
   LLB_LAUNCH_CHECK("t5_attn_kernel");
   return LLB_OK;
 }

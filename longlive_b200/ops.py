@@ -363,7 +363,7 @@ def embed_rows(table: torch.Tensor, ids: torch.Tensor, rows_per_seq: int,
 
 
 def t5_attention(qkv: torch.Tensor, batch: int, n_heads: int, seq_lens: torch.Tensor, pos_emb: torch.Tensor,
-                 bucket_lut: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 bucket_lut: torch.Tensor, out: Optional[torch.Tensor] = None, max_seq_len: int = 0) -> torch.Tensor:
     """T5Attention core on the fused projection output qkv [batch * rows_per_seq, 3 * n_heads * 64];
     seq_lens int32 [batch] (device), pos_emb bf16 [num_buckets, n_heads], bucket_lut int32 [2 * center + 1]."""
     _req(qkv, "qkv"); _req(pos_emb, "pos_emb"); _req(seq_lens, "seq_lens", torch.int32)
@@ -374,7 +374,7 @@ def t5_attention(qkv: torch.Tensor, batch: int, n_heads: int, seq_lens: torch.Te
         out = torch.empty((rows, n_heads * 64), dtype=torch.bfloat16, device=qkv.device)
     _req(out, "out")
     rc = _lib.lib().llb_t5_attn(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), batch, rows // batch,
-                                n_heads, seq_lens.data_ptr(), pos_emb.data_ptr(), bucket_lut.data_ptr(),
+                                n_heads, max_seq_len, seq_lens.data_ptr(), pos_emb.data_ptr(), bucket_lut.data_ptr(),
                                 (bucket_lut.numel() - 1) // 2, _stream())
     _lib.check(rc, "llb_t5_attn")
     return out

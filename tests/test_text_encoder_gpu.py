@@ -100,7 +100,8 @@ def _attn_reference(qkv, B, H, lens, pos_emb, lut):
 
 
 @pytest.mark.parametrize("Lp,lens,H,scale", [(128, (128,), 2, 0.3), (128, (1, 37), 3, 0.5), (256, (256, 130), 2, 0.4),
-                                             (512, (512, 65, 300), 4, 0.25), (512, (200,), 64, 0.2)])
+                                             (512, (512, 65, 300), 4, 0.25), (512, (200,), 64, 0.2),
+                                             (512, (512, 1), 40, 0.3)])   # the last two use 256-row CTAs
 def test_t5_attn_kernel(Lp, lens, H, scale):
     ops = _ops()
     from longlive_b200.text_encoder import relative_position_buckets
@@ -118,6 +119,8 @@ def test_t5_attn_kernel(Lp, lens, H, scale):
         err = rel_l2(out[b * Lp:(b + 1) * Lp], ref[b * Lp:(b + 1) * Lp])
         assert err < 8e-3, (b, n, err)
     assert torch.isfinite(out.float()).all()
+    # shared memory sized to the longest prompt instead of the padded row count: same result
+    assert torch.equal(ops.t5_attention(qkv, B, H, lens_t, pos, lut, max_seq_len=max(lens)), out)
     # masked keys contribute nothing: garbage (even NaN) in their K / V rows must not change the result
     if min(lens) < Lp:
         q2 = qkv.clone().view(B, Lp, -1)
