@@ -233,7 +233,12 @@ struct SegIter {
 // kPoly: every kPoly-th pair of probabilities is exponentiated with exp2_poly2 instead of MUFU
 // (0 = MUFU only).  MUFU.EX2 runs at 16/clk/SM, exactly the rate the two S tiles are produced at, so
 // moving a quarter of the work to the FMA pipe takes the special-function unit off the critical path.
-template <bool kPTmem, int kPoly>
+// kHalf (TMEM-P only): every 128-key tile is processed as two 64-key halves A | B with their own S buffers
+// (columns [0,64) and [64,128) of the tile's S region, P_h over the first 32 columns of S_h) and their own
+// barriers.  QK_B is issued right behind QK_A, and the next tile's QK_A right behind PV_A, so while a softmax
+// warpgroup works on one half the tensor core already refills the other: the per-Q-tile chain
+// QK -> softmax -> PV that bounds the whole-tile schedule is cut in two overlapping chains per Q tile.
+template <bool kPTmem, int kPoly, bool kHalf>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -258,6 +263,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
   auto sfree_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };
   auto phalf_bar = sfree_bar;  // TMEM-P path (no s_free there): first half of P_t(j) is in TMEM
+  auto sfullb_bar = [&](int s) { return bar_base + 8u * (15 + 2 * kStages + s); };  // kHalf: S_t half B ready
+  auto oadone_bar = [&](int s) { return bar_base + 8u * (17 + 2 * kStages + s); };  // kHalf: PV_t half A complete
   const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
@@ -277,6 +284,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(odone_bar(s), 1);
       mbar_init(ofree_bar(s), 4);
       mbar_init(sfree_bar(s), 4);
+      mbar_init(sfullb_bar(s), 1);
+      mbar_init(oadone_bar(s), 1);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
@@ -409,7 +418,143 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
         uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
 
-        if constexpr (kPTmem) {
+        if constexpr (kPTmem && kHalf) {
+          constexpr uint32_t idesc_qk64 = umma_idesc_bf16(128, 64, 0, 0);
+          // S_t half h (64 keys): D = columns [h*64, h*64+64) of the tile's S region, B = key rows h*64.. of K
+          auto issue_qk_half = [&](int t, uint32_t kst, int h) {
+            const uint32_t qa = q_base + t * kTileBytes;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+              umma_ss(tmem_base + t * 128 + h * 64, umma_desc_kmajor(qa + o),
+                      umma_desc_kmajor(kst + h * 8192 + o), idesc_qk64, kk != 0);
+            }
+          };
+          // O_t += P_t half h (bf16 in the first 32 columns of S_t half h) x V rows h*64 .. h*64+63
+          auto issue_pv_half = [&](int t, uint32_t vst, bool first, int h) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t bdesc = umma_desc_mnmajor(vst + (h * 4 + kk) * 2048, kBoxBytes);
+              umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + h * 64 + kk * 8, bdesc, idesc_pv,
+                      (first && kk == 0) ? 0u : 1u);
+            }
+          };
+          for (; sg.ok; sg.next()) {
+            const int head = sg.item / p.n_pairs;
+            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+            const bool has1 = q_row0 + 128 < p.Lq;
+            const int nt = sg.t1 - sg.t0;
+            mbar_wait(qfull_bar(0), qph0);
+            qph0 ^= 1;
+            if (has1) {
+              mbar_wait(qfull_bar(1), qph1);
+              qph1 ^= 1;
+            }
+            mbar_wait(kvfull_bar(stage), phase);
+            tc_fence_after();
+            uint32_t kst = kv_base + stage * kTileBytes;
+            if (elect_one()) {
+              issue_qk_half(0, kst, 0);
+              umma_commit(sfull_bar(0));
+              if (has1) {
+                issue_qk_half(1, kst, 0);
+                umma_commit(sfull_bar(1));
+              }
+              issue_qk_half(0, kst, 1);
+              umma_commit(sfullb_bar(0));
+              if (nt == 1) umma_commit(qempty_bar(0));
+              if (has1) {
+                issue_qk_half(1, kst, 1);
+                umma_commit(sfullb_bar(1));
+                if (nt == 1) umma_commit(qempty_bar(1));
+              }
+              umma_commit(kvempty_bar(stage));
+            }
+            __syncwarp();
+            advance();
+            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
+            oseg0++;
+            if (has1) {
+              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
+              oseg1++;
+            }
+            for (int j = 0; j < nt; ++j) {
+              const bool more = j + 1 < nt;
+              const bool last_qk = j + 2 == nt;
+              const int vstage = stage;
+              mbar_wait(kvfull_bar(stage), phase);
+              const uint32_t vst = kv_base + stage * kTileBytes;
+              advance();
+              int kstage = 0;
+              if (more) {
+                kstage = stage;
+                mbar_wait(kvfull_bar(stage), phase);
+                kst = kv_base + stage * kTileBytes;
+                advance();
+              }
+              // half A of both tiles: O_t += P_tA(j) V_j[0:64]; S_tA(j+1) = Q_t K_{j+1}[0:64]^T
+              mbar_wait(phalf_bar(0), pcnt0 & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_pv_half(0, vst, j == 0, 0);
+                umma_commit(oadone_bar(0));
+                if (more) {
+                  issue_qk_half(0, kst, 0);
+                  umma_commit(sfull_bar(0));
+                }
+              }
+              __syncwarp();
+              if (has1) {
+                mbar_wait(phalf_bar(1), pcnt1 & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                  issue_pv_half(1, vst, j == 0, 0);
+                  umma_commit(oadone_bar(1));
+                  if (more) {
+                    issue_qk_half(1, kst, 0);
+                    umma_commit(sfull_bar(1));
+                  }
+                }
+                __syncwarp();
+              }
+              // half B
+              mbar_wait(pfull_bar(0), pcnt0 & 1);
+              pcnt0++;
+              tc_fence_after();
+              if (elect_one()) {
+                issue_pv_half(0, vst, false, 1);
+                umma_commit(odone_bar(0));
+                if (more) {
+                  issue_qk_half(0, kst, 1);
+                  umma_commit(sfullb_bar(0));
+                  if (last_qk) umma_commit(qempty_bar(0));
+                }
+                if (!has1) {
+                  umma_commit(kvempty_bar(vstage));
+                  if (more) umma_commit(kvempty_bar(kstage));
+                }
+              }
+              __syncwarp();
+              if (has1) {
+                mbar_wait(pfull_bar(1), pcnt1 & 1);
+                pcnt1++;
+                tc_fence_after();
+                if (elect_one()) {
+                  issue_pv_half(1, vst, false, 1);
+                  umma_commit(odone_bar(1));
+                  umma_commit(kvempty_bar(vstage));
+                  if (more) {
+                    issue_qk_half(1, kst, 1);
+                    umma_commit(sfullb_bar(1));
+                    if (last_qk) umma_commit(qempty_bar(1));
+                    umma_commit(kvempty_bar(kstage));
+                  }
+                }
+                __syncwarp();
+              }
+            }
+          }
+        } else if constexpr (kPTmem) {
           for (; sg.ok; sg.next()) {
             const int head = sg.item / p.n_pairs;
             const int q_row0 = (sg.item - head * p.n_pairs) * 256;
@@ -645,6 +790,86 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
         int row0, valid;
         kv_it.get(row0, valid);
+        if constexpr (kPTmem && kHalf) {
+          const uint32_t ph = cnt & 1;
+          cnt++;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(h == 0 ? sfull_bar(t) : sfullb_bar(t), ph);
+            tc_fence_after();
+            uint32_t sv[2][32];
+            tmem_ld32(t_s + h * 64, sv[0]);
+            tmem_ld32(t_s + h * 64 + 32, sv[1]);
+            tmem_wait_ld();
+            if (valid < h * 64 + 64) {
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (h * 64 + cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+              mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+            }
+            const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+            const bool need = (m_new - m_used) * c > 8.0f;
+            if (__any_sync(0xffffffffu, need)) {
+              const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first half (m_used = -inf)
+              if (j > sg.t0 || h == 1) {
+                // O must be stable: every PV issued so far for this Q tile has to be complete.  Before half A
+                // that is PV_B of the previous key tile, before half B it is PV_A of this one.
+                if (h == 0) mbar_wait(odone_bar(t), ph ^ 1);
+                else mbar_wait(oadone_bar(t), ph);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                  uint32_t ov[32];
+                  tmem_ld32(t_o + cc * 32, ov);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+                  tmem_st32(t_o + cc * 32, ov);
+                }
+                tmem_wait_st();
+              }
+              l *= f;
+              m_used = m_new;
+            }
+            const float neg = -m_used * c;
+            const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
+            float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 tt = __ffma2_rn(
+                    make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
+                float2 pp;
+                if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
+                  pp = exp2_poly2(tt);
+                } else {
+                  pp.x = ex2_approx(tt.x);
+                  pp.y = ex2_approx(tt.y);
+                }
+                if (i & 1) lb = __fadd2_rn(lb, pp);
+                else la = __fadd2_rn(la, pp);
+                pk[i] = pack_bf16x2(pp.x, pp.y);
+              }
+              tmem_st16(t_s + h * 64 + cc * 16, pk);
+            }
+            la = __fadd2_rn(la, lb);
+            l += la.x + la.y;
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h == 0 ? phalf_bar(t) : pfull_bar(t));
+          }
+          continue;
+        }
         mbar_wait(sfull_bar(t), cnt & 1);
         cnt++;
         tc_fence_after();
@@ -861,13 +1086,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <bool kPTmem, int kPoly>
+template <bool kPTmem, int kPoly, bool kHalf = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
   using Cfg = AttnCfg<kPTmem>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly>,
+    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly, kHalf>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -896,7 +1121,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly, kHalf>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -959,7 +1184,13 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   // variant bit 0: P through shared memory instead of TMEM; bit 1: MUFU-only exp2 (no polynomial);
   // bit 2: hand P to the MMA warp in two 64-key halves (TMEM-P path; measured 1.5 % slower on the
   // steady-state shape, 5 % faster on the 18720 x 18720 recache shape - off by default)
+  // bit 3: half-tile pipeline (TMEM-P path): two 64-key halves per key tile with their own S buffers and barriers
   p.split_p = (variant & 4) ? 1 : 0;
+  if ((variant & 8) && !(variant & 1)) {
+    p.split_p = 0;
+    return (variant & 2) ? launch_attn<true, 0, true>(tq, tk, tv, p, grid, s)
+                         : launch_attn<true, 4, true>(tq, tk, tv, p, grid, s);
+  }
   switch (variant & 3) {
     case 1: return launch_attn<false, 4>(tq, tk, tv, p, grid, s);
     case 2: return launch_attn<true, 0>(tq, tk, tv, p, grid, s);
