@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllb200.so")
+# LLB200_LIB: alternative build of the same library (tools/attn_debug_sweep.py times instrumented builds)
+LIB_PATH = os.environ.get("LLB200_LIB") or os.path.join(_HERE, "libllb200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 LLB_MAX_SEGS = 4

@@ -41,8 +41,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+// Timing experiments only (tools/attn_debug_sweep.py builds one library per value; results are garbage when != 0):
+// 1 no K/V TMA after the first ring fill, 2 no QK MMAs, 4 no PV MMAs, 8 no exp2, 16 no row max, 32 no S read from
+// TMEM, 64 no P write to TMEM, 128 no softmax arithmetic at all.  The shipped library is built with 0.
+#ifndef LLB_ATTN_DBG
+#define LLB_ATTN_DBG 0
+#endif
+
 namespace llb {
 
+constexpr int kDbg = LLB_ATTN_DBG;
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
@@ -326,6 +334,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         uint32_t qph0 = 0, qph1 = 0;
+        [[maybe_unused]] int dbg_loaded = 0;
         for (; sg.ok; sg.next()) {
           const int head = sg.item / p.n_pairs;
           const int q_row0 = (sg.item - head * p.n_pairs) * 256;
@@ -347,9 +356,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           auto load_tile = [&](const CUtensorMap* tm, int row0) {
             mbar_wait(kvempty_bar(stage), phase ^ 1);
             const uint32_t dst = kv_base + stage * kTileBytes;
-            mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
-            tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
-            tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
+            if ((kDbg & 1) && dbg_loaded >= kStages) {
+              mbar_arrive(kvfull_bar(stage));
+            } else {
+              mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
+              tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
+              tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
+              if (kDbg & 1) ++dbg_loaded;
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           };
           kv_it.seek(sg.t0);
@@ -385,9 +399,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // ------------------------------------------------------------------ MMA issuer
       // The whole warp runs this loop (waits included); one elected lane issues the tcgen05 ops.
       {
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, (kDbg & 256) ? 16 : 128, 0, 0);  // 256: same MMA count, 1/8 of the work
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, (kDbg & 256) ? 16 : 128, 0, 1);
         auto issue_qk = [&](int t, uint32_t kst) {
+          if (kDbg & 2) return;
           const uint32_t qa = q_base + t * kTileBytes;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -397,6 +412,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         };
         auto issue_pv = [&](int t, uint32_t vst, bool first, int kk0, int kk1) {
+          if (kDbg & 4) return;
 #pragma unroll
           for (int kk = kk0; kk < kk1; ++kk) {
             // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA
@@ -621,7 +637,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               if (elect_one()) {
                 if (p.split_p) issue_pv(0, vst, false, 4, 8);
                 else issue_pv(0, vst, j == 0, 0, 8);
-                umma_commit(odone_bar(0));
+                if (!(kDbg & 512) || !more) umma_commit(odone_bar(0));
                 if (more) {
                   issue_qk(0, kst);
                   umma_commit(sfull_bar(0));
@@ -646,7 +662,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 if (elect_one()) {
                   if (p.split_p) issue_pv(1, vst, false, 4, 8);
                   else issue_pv(1, vst, j == 0, 0, 8);
-                  umma_commit(odone_bar(1));
+                  if (!(kDbg & 512) || !more) umma_commit(odone_bar(1));
                   umma_commit(kvempty_bar(vstage));
                   if (more) {
                     issue_qk(1, kst);
@@ -775,6 +791,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_o = tmem_base + lane_off + 256 + t * 128;
     const float c = p.scale_log2;
     uint32_t cnt = 0;  // kv tiles processed by this warpgroup (s_full / o_done phase)
+    [[maybe_unused]] uint32_t segcnt = 0;
     const int64_t ws_row = static_cast<int64_t>(t) * 128 + row_in_tile;
     LLB_ATTN_INIT_WORK();
 
@@ -874,9 +891,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         cnt++;
         tc_fence_after();
         uint32_t sv[4][32];
+        if constexpr ((kDbg & 32) != 0) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
-        tmem_wait_ld();
+          for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[cc][i] = __float_as_uint(static_cast<float>(j + i));
+        } else {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
+          tmem_wait_ld();
+        }
         bool prev_pv_done = kPTmem || j == sg.t0;  // TMEM-P: S_t(j) ready already implies PV_t(j-1) done
         if constexpr (!kPTmem) {
           // S_t(j) now lives in registers: let the MMA warp overwrite it with S_t(j+1)
@@ -892,12 +916,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               if (cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if constexpr ((kDbg & 16) != 0) {
+          mx0 = __uint_as_float(sv[0][0]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+          for (int i = 0; i < 32; ++i) {
+            mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+            mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
+            mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
+          }
         }
         const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
         // lazy rescale: only when the max moved by more than 2^8 in the exp2 domain
@@ -936,7 +964,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const float2 tt = __ffma2_rn(
                 make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
             float2 pp;
-            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
+            if constexpr ((kDbg & 128) != 0) {
+              pk[i] = sv[cc][2 * i];
+              continue;
+            }
+            if constexpr ((kDbg & 8) != 0) {
+              pp = tt;
+            } else if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
               pp = exp2_poly2(tt);
             } else {
               pp.x = ex2_approx(tt.x);
@@ -947,7 +981,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             pk[i] = pack_bf16x2(pp.x, pp.y);
           }
           if constexpr (kPTmem) {
-            tmem_st16(t_s + cc * 16, pk);
+            if constexpr ((kDbg & 64) != 0) {
+              if (pk[3] == 0x12345678u) l += 1.0f;  // keeps pk alive without the TMEM store
+            } else {
+              tmem_st16(t_s + cc * 16, pk);
+            }
             if (cc == 1 && p.split_p) {
               // keys 0..63 of P_t(j) are complete: the MMA warp can start PV on them now
               tmem_wait_st();
@@ -983,7 +1021,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (lane == 0) mbar_arrive(pfull_bar(t));
       }
       // ---- segment epilogue
-      mbar_wait(odone_bar(t), (cnt - 1) & 1);
+      if constexpr ((kDbg & 512) != 0) {
+        mbar_wait(odone_bar(t), segcnt & 1);
+        segcnt++;
+      } else {
+        mbar_wait(odone_bar(t), (cnt - 1) & 1);
+      }
       tc_fence_after();
       const bool tail_part = sg.in_remainder() && sg.t0 > 0;     // earlier kv tiles live in CTA blockIdx.x - 1
       const bool head_part = sg.in_remainder() && sg.t1 < sg.T;  // later kv tiles live in CTA blockIdx.x + 1
