@@ -51,6 +51,19 @@
 namespace llb {
 
 constexpr int kDbg = LLB_ATTN_DBG;
+#if (LLB_ATTN_DBG & 2048)
+// 2048: CTA 0 time-stamps its hand-offs (clock64, first kTsSteps key tiles): [0] WG0 sees S ready, [1] WG0 hands P over,
+// [2] MMA warp sees P_0, [3] MMA warp has issued PV_0 + QK_0, [4] MMA warp sees P_1, [5] has issued PV_1 + QK_1,
+// [6] WG1 sees S ready, [7] WG1 hands P over
+constexpr int kTsSteps = 512;
+__device__ long long g_attn_ts[8][kTsSteps];
+#define LLB_TS(slot, idx)                                                              \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && lane == 0 && (idx) < kTsSteps) g_attn_ts[slot][idx] = clock64(); \
+  } while (0)
+#else
+#define LLB_TS(slot, idx) do { } while (0)
+#endif
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
@@ -632,6 +645,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 __syncwarp();
               }
               mbar_wait(pfull_bar(0), pcnt0 & 1);
+              LLB_TS(2, pcnt0);
               pcnt0++;
               tc_fence_after();
               if (elect_one()) {
@@ -649,6 +663,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 }
               }
               __syncwarp();
+              LLB_TS(3, pcnt0 - 1);
               if (has1) {
                 if (p.split_p) {
                   mbar_wait(phalf_bar(1), pcnt1 & 1);
@@ -657,6 +672,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                   __syncwarp();
                 }
                 mbar_wait(pfull_bar(1), pcnt1 & 1);
+                LLB_TS(4, pcnt1);
                 pcnt1++;
                 tc_fence_after();
                 if (elect_one()) {
@@ -672,6 +688,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                   }
                 }
                 __syncwarp();
+                LLB_TS(5, pcnt1 - 1);
               }
             }
           }
@@ -888,6 +905,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           continue;
         }
         mbar_wait(sfull_bar(t), cnt & 1);
+        if (q == 0) LLB_TS(t == 0 ? 0 : 6, cnt);
         cnt++;
         tc_fence_after();
         uint32_t sv[4][32];
@@ -1018,6 +1036,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
+        if (q == 0) LLB_TS(t == 0 ? 1 : 7, cnt - 1);
         if (lane == 0) mbar_arrive(pfull_bar(t));
       }
       // ---- segment epilogue
@@ -1171,6 +1190,12 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 
 }  // namespace llb
 
+#if (LLB_ATTN_DBG & 2048)
+extern "C" int llb_attn_debug_ts(long long* host_buf) {  // [8][kTsSteps], instrumented builds only
+  return cudaMemcpyFromSymbol(host_buf, llb::g_attn_ts, sizeof(llb::g_attn_ts)) == cudaSuccess ? llb::kTsSteps : -1;
+}
+#endif
+
 extern "C" int64_t llb_attn_workspace_bytes(void) {
   const int sms = llb::device_sm_count();
   return static_cast<int64_t>(sms > 0 ? sms : 148) * llb::kWsPerCta;
@@ -1234,6 +1259,17 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     return (variant & 2) ? launch_attn<true, 0, true>(tq, tk, tv, p, grid, s)
                          : launch_attn<true, 4, true>(tq, tk, tv, p, grid, s);
   }
+#ifdef LLB_ATTN_POLY_SWEEP
+  // experiment builds only: LLB_ATTN_POLY = n sends every n-th probability pair through the polynomial (1 = all of them)
+  if (const char* e = getenv("LLB_ATTN_POLY")) {
+    switch (atoi(e)) {
+      case 1: return launch_attn<true, 1>(tq, tk, tv, p, grid, s);
+      case 2: return launch_attn<true, 2>(tq, tk, tv, p, grid, s);
+      case 3: return launch_attn<true, 3>(tq, tk, tv, p, grid, s);
+      default: break;
+    }
+  }
+#endif
   switch (variant & 3) {
     case 1: return launch_attn<false, 4>(tq, tk, tv, p, grid, s);
     case 2: return launch_attn<true, 0>(tq, tk, tv, p, grid, s);
