@@ -56,7 +56,7 @@ constexpr int kDbg = LLB_ATTN_DBG;
 // [2] MMA warp sees P_0, [3] MMA warp has issued PV_0 + QK_0, [4] MMA warp sees P_1, [5] has issued PV_1 + QK_1,
 // [6] WG1 sees S ready, [7] WG1 hands P over
 constexpr int kTsSteps = 512;
-__device__ long long g_attn_ts[8][kTsSteps];
+__device__ long long g_attn_ts[12][kTsSteps];  // [8] S in registers, [9] row max known, [10] all exp2 / P stores issued, [11] wait::st done (WG0)
 #define LLB_TS(slot, idx)                                                              \
   do {                                                                                  \
     if (blockIdx.x == 0 && lane == 0 && (idx) < kTsSteps) g_attn_ts[slot][idx] = clock64(); \
@@ -919,6 +919,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
           tmem_wait_ld();
         }
+        if (q == 0 && t == 0) LLB_TS(8, cnt - 1);
         bool prev_pv_done = kPTmem || j == sg.t0;  // TMEM-P: S_t(j) ready already implies PV_t(j-1) done
         if constexpr (!kPTmem) {
           // S_t(j) now lives in registers: let the MMA warp overwrite it with S_t(j+1)
@@ -972,6 +973,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           m_used = m_new;
         }
         const float neg = -m_used * c;
+        if (q == 0 && t == 0) LLB_TS(9, cnt - 1);
         const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1029,8 +1031,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         la = __fadd2_rn(la, lb);
         l += la.x + la.y;
+        if (q == 0 && t == 0) LLB_TS(10, cnt - 1);
         if constexpr (kPTmem) {
           tmem_wait_st();
+          if (q == 0 && t == 0) LLB_TS(11, cnt - 1);
         } else {
           fence_proxy_async_smem();
         }
@@ -1191,7 +1195,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }  // namespace llb
 
 #if (LLB_ATTN_DBG & 2048)
-extern "C" int llb_attn_debug_ts(long long* host_buf) {  // [8][kTsSteps], instrumented builds only
+extern "C" int llb_attn_debug_ts(long long* host_buf) {  // [12][kTsSteps], instrumented builds only
   return cudaMemcpyFromSymbol(host_buf, llb::g_attn_ts, sizeof(llb::g_attn_ts)) == cudaSuccess ? llb::kTsSteps : -1;
 }
 #endif

@@ -41,10 +41,10 @@ for _ in range(3):
     ops.attention(q, k, v, sp, n_heads=H, out=out)
 torch.cuda.synchronize()
 lib = _lib.lib()
-buf = (C.c_longlong * (8 * 512))()
+buf = (C.c_longlong * (12 * 512))()
 lib.llb_attn_debug_ts.restype = C.c_int
 n = lib.llb_attn_debug_ts(buf)
-ts = [[buf[s * 512 + i] for i in range(512)] for s in range(8)]
+ts = [[buf[s * 512 + i] for i in range(512)] for s in range(12)]
 names = ["wg0_S_seen", "wg0_P_handed", "mma_P0_seen", "mma_0_issued", "mma_P1_seen", "mma_1_issued", "wg1_S_seen", "wg1_P_handed"]
 t0 = ts[0][20]
 rows = []
@@ -59,6 +59,11 @@ summary = {
     "P0 handed -> MMA warp sees it": avg(lambda i: ts[2][i] - ts[1][i]),
     "MMA warp issue PV0 + QK0 (+commits)": avg(lambda i: ts[3][i] - ts[2][i]),
     "MMA issued 0 -> WG0 sees next S (tensor execution + commit + wake)": avg(lambda i: ts[0][i + 1] - ts[3][i]),
+    "  wg0: S seen -> S in registers (tcgen05.ld + wait)": avg(lambda i: ts[8][i] - ts[0][i]),
+    "  wg0: -> row max / rescale decision": avg(lambda i: ts[9][i] - ts[8][i]),
+    "  wg0: -> exp2, sums, bf16 pack, P stores issued": avg(lambda i: ts[10][i] - ts[9][i]),
+    "  wg0: -> tcgen05.wait::st": avg(lambda i: ts[11][i] - ts[10][i]),
+    "  wg0: -> fence, syncwarp, arrive": avg(lambda i: ts[1][i] - ts[11][i]),
     "wg1_softmax": avg(lambda i: ts[7][i] - ts[6][i]),
     "P1 handed -> MMA warp sees it": avg(lambda i: ts[4][i] - ts[7][i]),
     "MMA warp issue PV1 + QK1 (+commits)": avg(lambda i: ts[5][i] - ts[4][i]),
