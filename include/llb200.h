@@ -181,7 +181,8 @@ int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, floa
  *   The attended keys are the union of physical row ranges listed in seg_dev
  *   (llb_step_params.n_attn_segs / attn_start / attn_len, device memory).
  *   variant: 0 = default; measured alternatives kept for comparison (same results): bit 0 P through
- *   shared memory, bit 1 MUFU-only exp2, bit 2 P handed over in two halves, bit 3 half-tile (64-key) pipeline.
+ *   shared memory, bit 1 MUFU-only exp2, bit 2 P handed over in two halves, bit 3 half-tile (64-key) pipeline,
+ *   bit 4 two softmax warpgroups per Q tile.
  * ------------------------------------------------------------------------------------------ */
 int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                  int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,

@@ -75,11 +75,16 @@ constexpr int64_t kWsMlBytes = 2ll * 128 * 8;
 constexpr int64_t kWsFlagBytes = 2ll * 128 * 4;
 constexpr int64_t kWsPerCta = kWsOBytes + kWsMlBytes + kWsFlagBytes;
 
-template <bool kPTmem>
+// kWide: two softmax warpgroups per Q tile (640 threads): each thread owns half a row (64 of the 128 key columns), the
+// row maximum is exchanged through shared memory; one K/V stage less makes room for the exchange buffer.
+template <bool kPTmem, bool kWide = false>
 struct AttnCfg {
-  static constexpr int kStages = kPTmem ? 5 : 3;
+  static constexpr int kStages = kPTmem ? (kWide ? 4 : 5) : 3;
+  static constexpr int kThreads = kWide ? 640 : kAttnThreads;
+  static constexpr int kSoftmaxWarps = kWide ? 16 : 8;
+  static constexpr int kXchgBytes = kWide ? 2 * 2 * 2 * 128 * 4 : 0;  // [tile][half][buffer][row] float
   static constexpr int kSmemBytes =
-      1024 + 2 * kTileBytes + (kPTmem ? 0 : 2 * kTileBytes) + kStages * kTileBytes + 256;
+      1024 + 2 * kTileBytes + (kPTmem ? 0 : 2 * kTileBytes) + kStages * kTileBytes + 256 + kXchgBytes;
 };
 
 struct AttnParams {
@@ -259,12 +264,14 @@ struct SegIter {
 // barriers.  QK_B is issued right behind QK_A, and the next tile's QK_A right behind PV_A, so while a softmax
 // warpgroup works on one half the tensor core already refills the other: the per-Q-tile chain
 // QK -> softmax -> PV that bounds the whole-tile schedule is cut in two overlapping chains per Q tile.
-template <bool kPTmem, int kPoly, bool kHalf>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <bool kPTmem, int kPoly, bool kHalf, bool kWide = false>
+__global__ void __maxnreg__((kWide ? 96 : 168))  // = 65536 / threads, rounded down to the allocation unit
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using Cfg = AttnCfg<kPTmem>;
+  using Cfg = AttnCfg<kPTmem, kWide>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kMmaWarp = Cfg::kSoftmaxWarps, kTmaWarp = Cfg::kSoftmaxWarps + 1;
+  static_assert(!kWide || (kPTmem && !kHalf), "kWide is built on the whole-tile TMEM-P schedule");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -289,11 +296,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
+  [[maybe_unused]] float* xchg = reinterpret_cast<float*>(bar_gen + 256);  // kWide: row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -301,9 +309,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(qfull_bar(s), 1);
       mbar_init(qempty_bar(s), 1);
       mbar_init(sfull_bar(s), 1);
-      mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
+      mbar_init(pfull_bar(s), kWide ? 8 : 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
-      mbar_init(ofree_bar(s), 4);
+      mbar_init(ofree_bar(s), kWide ? 8 : 4);
       mbar_init(sfree_bar(s), 4);
       mbar_init(sfullb_bar(s), 1);
       mbar_init(oadone_bar(s), 1);
@@ -314,7 +322,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -338,9 +346,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // Register re-distribution: the kernel launches at 168 regs/thread (65536 / 384); the two softmax
   // warpgroups hold a full 128-column S row per thread and take 208, the MMA/TMA warpgroup keeps 88
   // ((168-88)*128 registers released >= (208-168)*256 requested, so the inc never blocks).
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    if (warp == 9) {
+  if (warp >= kMmaWarp) {
+    // kWide: 640 threads launch at 96 registers; this warpgroup gives back (96-64)*128 = 4096, exactly the
+    // (104-96)*512 the four softmax warpgroups ask for (setmaxnreg.inc only draws on what the CTA itself released;
+    // 576 threads at 112 registers do not launch: warps are allocated four at a time)
+    if constexpr (kWide) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == kTmaWarp) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
         LLB_ATTN_INIT_WORK();
@@ -408,7 +420,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
-    } else if (warp == 8) {
+    } else if (warp == kMmaWarp) {
       // ------------------------------------------------------------------ MMA issuer
       // The whole warp runs this loop (waits included); one elected lane issues the tcgen05 ops.
       {
@@ -798,6 +810,219 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else {
+    if constexpr (kWide) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // -------------------------------------------------------------------- softmax warps, two warpgroups per Q tile
+    // warps 0-3 / 4-7: Q tile 0, key columns [0,64) / [64,128) of every key tile; warps 8-11 / 12-15: Q tile 1.
+    // Both warpgroups of a tile wait on the same s_full barrier; the thread pair of a row exchanges its half-row
+    // maximum through shared memory (named barrier 1 + t, 256 threads, buffers alternate per key tile), so both
+    // take the same rescale decision; each rescales / drains its own 64 columns of O_t.
+    const int t = warp >> 3;
+    const int hf = (warp >> 2) & 1;
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + t * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + t * 128 + hf * 64;
+    const float c = p.scale_log2;
+    uint32_t cnt = 0;
+    const int64_t ws_row = static_cast<int64_t>(t) * 128 + row_in_tile;
+    float* x_own = xchg + ((t * 2 + hf) * 2) * 128 + row_in_tile;         // [buffer 0], +128 = buffer 1
+    const float* x_oth = xchg + ((t * 2 + (hf ^ 1)) * 2) * 128 + row_in_tile;
+    auto pair_sync = [&]() {
+      if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    LLB_ATTN_INIT_WORK();
+
+    for (; sg.ok; sg.next()) {
+      const int head = sg.item / p.n_pairs;
+      const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+      const bool has1 = q_row0 + 128 < p.Lq;
+      if (t == 1 && !has1) continue;
+      const int grow = q_row0 + t * 128 + row_in_tile;
+      float m_used = -INFINITY;
+      float l = 0.f;  // sum over this thread's 64 columns only; the halves are added in the segment epilogue
+      kv_it.seek(sg.t0);
+      for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
+        int row0, valid;
+        kv_it.get(row0, valid);
+        const uint32_t buf = (cnt & 1) * 128;
+        mbar_wait(sfull_bar(t), cnt & 1);
+        cnt++;
+        tc_fence_after();
+        uint32_t sv[2][32];
+        tmem_ld32(t_s + hf * 64, sv[0]);
+        tmem_ld32(t_s + hf * 64 + 32, sv[1]);
+        tmem_wait_ld();
+        if (valid < hf * 64 + 64) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (hf * 64 + cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+        }
+        x_own[buf] = fmaxf(mx0, mx1);
+        // also orders the partner's S reads before this thread's P stores (P overlays S columns [0,64))
+        pair_sync();
+        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), x_oth[buf]));
+        const bool need = (m_new - m_used) * c > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used = -inf)
+          if (j > sg.t0) {
+            // S_t(j) ready implies PV_t(j-1) complete (issued before QK_t(j)): O is stable.  16 columns at a time:
+            // the half row of S stays live across this (rare) path and the register budget is 112
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t ov[16];
+              tmem_ld16(t_o + cc * 16, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+              tmem_st16(t_o + cc * 16, ov);
+            }
+            tmem_wait_st();
+          }
+          l *= f;
+          m_used = m_new;
+        }
+        const float neg = -m_used * c;
+        const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 tt = __ffma2_rn(
+                make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
+            float2 pp;
+            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
+              pp = exp2_poly2(tt);
+            } else {
+              pp.x = ex2_approx(tt.x);
+              pp.y = ex2_approx(tt.y);
+            }
+            if (i & 1) lb = __fadd2_rn(lb, pp);
+            else la = __fadd2_rn(la, pp);
+            pk[i] = pack_bf16x2(pp.x, pp.y);
+          }
+          tmem_st16(t_s + hf * 32 + cc * 16, pk);  // P: keys hf*64 + cc*32 .. +31 -> 16 packed columns
+        }
+        la = __fadd2_rn(la, lb);
+        l += la.x + la.y;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar(t));
+      }
+      // ---- segment epilogue: each thread owns output columns [hf*64, hf*64 + 64) of its row
+      mbar_wait(odone_bar(t), (cnt - 1) & 1);
+      tc_fence_after();
+      x_own[0] = l;  // buffer 0 / 1 are both free here: the last exchange of the loop was read before pfull
+      pair_sync();
+      l += x_oth[0];
+      const bool tail_part = sg.in_remainder() && sg.t0 > 0;
+      const bool head_part = sg.in_remainder() && sg.t1 < sg.T;
+      const bool row_ok = grow < p.Lq;
+      float a_own = 1.0f, a_oth = 0.0f;
+      const float4* wo_in = nullptr;
+      uint32_t* flag_in = nullptr;
+      if (head_part && row_ok) {
+        uint8_t* wsb = p.workspace + static_cast<int64_t>(blockIdx.x + 1) * kWsPerCta;
+        flag_in = reinterpret_cast<uint32_t*>(wsb + kWsOBytes + kWsMlBytes) + ws_row;
+        uint32_t spins = 0;
+        uint64_t t_start = 0;
+        while (ld_acquire_u32(flag_in) == 0u) {
+          if ((++spins & 0xfffu) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > LLB_WAIT_TIMEOUT_NS) __trap();
+          }
+        }
+        const volatile float* mlp = reinterpret_cast<const volatile float*>(wsb + kWsOBytes) + 2 * ws_row;
+        const float m_oth = mlp[0], l_oth = mlp[1];
+        const float m = fmaxf(m_used, m_oth);
+        a_own = ex2_approx((m_used - m) * c);
+        a_oth = ex2_approx((m_oth - m) * c);
+        l = l * a_own + l_oth * a_oth;
+        m_used = m;
+        wo_in = reinterpret_cast<const float4*>(wsb) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
+      }
+      uint8_t* wsb_out = p.workspace + static_cast<int64_t>(blockIdx.x) * kWsPerCta;
+      float4* wo_out = reinterpret_cast<float4*>(wsb_out) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
+      if (!tail_part) {
+        const float inv = 1.0f / l;
+        a_own *= inv;
+        a_oth *= inv;
+      }
+      __nv_bfloat16* orow = p.out + static_cast<int64_t>(grow) * p.ldo + head * 128;
+      if (p.shard.n_ranks > 1 && row_ok) {
+        const int r = grow / p.shard.rows_per_rank;
+        orow = static_cast<__nv_bfloat16*>(p.shard.out_peers[r]) +
+               static_cast<int64_t>(grow - r * p.shard.rows_per_rank) * p.shard.ld_out + p.shard.head_col0 +
+               head * 128;
+      }
+#pragma unroll 1
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col = hf * 64 + c4 * 16;  // first of 16 output columns
+        uint32_t ov[16];
+        tmem_ld16(t_o + c4 * 16, ov);
+        tmem_wait_ld();
+        if (row_ok) {
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(ov[i]) * a_own;
+          if (wo_in != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 x = ld_cg_f4(wo_in + (col / 4 + i) * 128);
+              o[4 * i] += x.x * a_oth;
+              o[4 * i + 1] += x.y * a_oth;
+              o[4 * i + 2] += x.z * a_oth;
+              o[4 * i + 3] += x.w * a_oth;
+            }
+          }
+          if (tail_part) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              wo_out[(col / 4 + i) * 128] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(o[8 * i + 0], o[8 * i + 1]);
+              w.y = pack_bf16x2(o[8 * i + 2], o[8 * i + 3]);
+              w.z = pack_bf16x2(o[8 * i + 4], o[8 * i + 5]);
+              w.w = pack_bf16x2(o[8 * i + 6], o[8 * i + 7]);
+              *reinterpret_cast<uint4*>(orow + col + i * 8) = w;
+            }
+          }
+        }
+      }
+      // the flag of the merged partial is consumed, and our own partial published, by the hf == 0 thread of the
+      // row after BOTH halves are done with the workspace (their writes fenced, then the pair barrier)
+      if (tail_part) __threadfence();
+      pair_sync();
+      if (hf == 0) {
+        if (flag_in != nullptr) st_release_u32(flag_in, 0u);
+        if (tail_part && row_ok) {
+          reinterpret_cast<float2*>(wsb_out + kWsOBytes)[ws_row] = make_float2(m_used, l);
+          __threadfence();
+          st_release_u32(reinterpret_cast<uint32_t*>(wsb_out + kWsOBytes + kWsMlBytes) + ws_row, 1u);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ofree_bar(t));
+    }
+    } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // -------------------------------------------------------------------- softmax warps
     const int t = warp >> 2;  // Q tile handled by this warpgroup
@@ -1142,23 +1367,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(ofree_bar(t));
     }
+    }  // !kWide
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <bool kPTmem, int kPoly, bool kHalf = false>
+template <bool kPTmem, int kPoly, bool kHalf = false, bool kWide = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
-  using Cfg = AttnCfg<kPTmem>;
+  using Cfg = AttnCfg<kPTmem, kWide>;
   static bool attr_set = false;
   if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly, kHalf>,
+    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -1166,7 +1392,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   // partial-merge flag wait relies on
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kAttnThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -1187,7 +1413,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly, kHalf>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -1258,6 +1484,12 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   // steady-state shape, 5 % faster on the 18720 x 18720 recache shape - off by default)
   // bit 3: half-tile pipeline (TMEM-P path): two 64-key halves per key tile with their own S buffers and barriers
   p.split_p = (variant & 4) ? 1 : 0;
+  // bit 4: two softmax warpgroups per Q tile (640 threads, half a row per thread)
+  if ((variant & 16) && !(variant & 1)) {
+    p.split_p = 0;
+    return (variant & 2) ? launch_attn<true, 0, false, true>(tq, tk, tv, p, grid, s)
+                         : launch_attn<true, 4, false, true>(tq, tk, tv, p, grid, s);
+  }
   if ((variant & 8) && !(variant & 1)) {
     p.split_p = 0;
     return (variant & 2) ? launch_attn<true, 0, true>(tq, tk, tv, p, grid, s)
