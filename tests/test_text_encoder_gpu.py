@@ -264,3 +264,53 @@ def test_full_size_encoder_vs_oracle():
     # all 512 positions, no trimming
     out_full = enc(ids, mask, trim_padding=False)
     assert torch.equal(out_full, out)
+
+
+def test_interactive_pipeline_with_text_encoder_and_vae():
+    """The reference's interactive entry point end to end with every stage native: prompt strings -> umT5 encoder ->
+    denoising with a prompt switch (KV-recache) -> streaming VAE decoder -> pixels, on narrow models."""
+    from types import SimpleNamespace
+    from longlive_b200 import synth
+    from longlive_b200.model import CausalWanModel
+    from longlive_b200.pipeline import InteractiveCausalInferencePipeline
+    from longlive_b200.text_encoder import HashTokenizer, UMT5Encoder, WanTextEncoder
+    from longlive_b200.vae import WanVAEWrapper, WanVAEDecoder
+    from longlive_b200.wrapper import WanDiffusionWrapper
+    enc = UMT5Encoder(vocab=500, dim=128, dim_attn=128, dim_ffn=256, num_heads=2, num_layers=2, text_len=32,
+                      device=DEV, dtype=torch.bfloat16)
+    synth.random_init_t5_(enc, seed=0, q_gain=8.0, pos_gain=8.0)
+    te = WanTextEncoder(text_encoder=enc, tokenizer=HashTokenizer(seq_len=32, vocab_size=500))
+    model = CausalWanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=128, text_len=32,
+                           local_attn_size=4, sink_size=1, frame_seqlen=24)
+    synth.random_init_(model, seed=0)
+    gen = WanDiffusionWrapper(model=model.to(DEV).to(torch.bfloat16), timestep_shift=5.0)
+    vae = WanVAEWrapper(WanVAEDecoder(dim=16, z_dim=16))
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for name, prm in vae.model.named_parameters():
+            if prm.dim() > 1 and not name.endswith("gamma"):
+                prm.copy_(torch.randn(prm.shape, generator=g) / prm[0].numel() ** 0.5)
+    vae.model.to(DEV)
+
+    class MK(dict):
+        __getattr__ = dict.get
+    args = SimpleNamespace(denoising_step_list=[1000, 750, 500, 250], warp_denoising_step=True, num_frame_per_block=2,
+                           context_noise=0, global_sink=False,
+                           model_kwargs=MK(local_attn_size=4, sink_size=1, timestep_shift=5.0))
+    pipe = InteractiveCausalInferencePipeline(args, torch.device(DEV), generator=gen, text_encoder=te, vae=vae)
+
+    def renoise(like, block, step):   # deterministic re-noising so that two runs are comparable
+        gg = torch.Generator().manual_seed(1000 + 4 * block + step)
+        return torch.randn(like.shape, generator=gg).to(like.dtype).to(like.device)
+    pipe.renoise_fn = renoise
+    noise = torch.randn(1, 8, 16, 8, 12, generator=g).to(torch.bfloat16).to(DEV)
+    prompts = [["a red fox runs through the snow"], ["the fox stops and looks at the camera"]]
+    video, lat = pipe.inference(noise, text_prompts_list=prompts, switch_frame_indices=[4], return_latents=True)
+    assert lat.shape == noise.shape and torch.isfinite(lat.float()).all()
+    assert video.shape[0] == 1 and video.shape[2] == 3 and video.shape[-2:] == (64, 96)
+    assert video.shape[1] == 1 + 4 * 7 and float(video.min()) >= 0.0 and float(video.max()) <= 1.0
+    assert len(pipe.switch_log) == 1
+    # same noise, no switch: frames before the switch agree, frames after it differ
+    video2, lat2 = pipe.inference(noise, text_prompts_list=prompts[:1], switch_frame_indices=[], return_latents=True)
+    assert rel_l2(lat[:, :4], lat2[:, :4]) < 1e-6
+    assert rel_l2(lat[:, 4:], lat2[:, 4:]) > 1e-3
