@@ -154,6 +154,14 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
                   void* stream);
 
+/* Split-K form for skinny problems (the umT5 encoder's N = 4096 projections at 128-256 token rows stream 33-84 MB of
+ * weights through only 64 CTAs otherwise): k_splits partial products are written as fp32 to `workspace`
+ * (k_splits * M * N floats, caller-owned) and a second launch sums them and applies the epilogue
+ * (LLB_EPI_BIAS or LLB_EPI_BIAS_RES; `res` may alias `out`). */
+int llb_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
+                         int N, int K, int epilogue, const void* bias, const void* res, int64_t ld_res,
+                         int k_splits, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Optional FP8 linears (README.md:50 of the reference advertises "FP8 quantization" at 24.8 FPS but
  * ships no code for it, reports.md:24,39).  W8A8 with e4m3 operands on tcgen05 kind::f8f6f4:
  *   A8 [M,K] e4m3 with per-row scale a_scale[M] (dynamic, produced by llb_ln_modulate_fp8 /

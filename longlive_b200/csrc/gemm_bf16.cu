@@ -73,6 +73,8 @@ struct GemmParams {
   const __nv_bfloat16* res;
   int64_t ld_res;
   int num_m_tiles, num_n_tiles;  // pair mode: num_m_tiles counts 256-row tiles
+  int k_splits, kb_per_split;    // split-K (llb_gemm_bf16_splitk): tile t also selects k-blocks [ks * kb_per_split, ...)
+                                 // and its fp32 partial goes to slice ks of the workspace `out` points at
   const float* a_scale;  // fp8 path: per-row activation scale [M]
   const float* w_scale;  // fp8 path: per-output-channel weight scale [N]
 };
@@ -131,9 +133,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int worker = kPair ? (blockIdx.x >> 1) : blockIdx.x;
   const int num_workers = kPair ? (gridDim.x >> 1) : gridDim.x;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = tiles_mn * p.k_splits;
   constexpr int kKElems = kFp8 ? 128 : kBK;  // elements per k-block (always 128 bytes)
-  const int num_kb = (p.K + kKElems - 1) / kKElems;
+  const int num_kb_total = (p.K + kKElems - 1) / kKElems;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -174,11 +177,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        const int m_idx = tile % p.num_m_tiles;
-        const int n_idx = tile / p.num_m_tiles;
+        const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
+        const int m_idx = tmn % p.num_m_tiles;
+        const int n_idx = tmn / p.num_m_tiles;
         const int a_row = kPair ? (m_idx * 2 + static_cast<int>(cta_rank)) * kBM : m_idx * kBM;
         const int b_row = n_idx * BN + (kPair ? static_cast<int>(cta_rank) * (BN / 2) : 0);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = ks * p.kb_per_split;
+        const int num_kb = min(p.kb_per_split, num_kb_total - kb0);
+        for (int kb = kb0; kb < kb0 + num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kStageA;
@@ -213,6 +219,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        const int num_kb = min(p.kb_per_split, num_kb_total - (tile / tiles_mn) * p.kb_per_split);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -262,8 +269,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
     int it = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
-      const int m_idx = tile % p.num_m_tiles;
-      const int n_idx = tile / p.num_m_tiles;
+      const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
+      const int m_idx = tmn % p.num_m_tiles;
+      const int n_idx = tmn / p.num_m_tiles;
       const int row_base = (kPair ? (m_idx * 2 + static_cast<int>(cta_rank)) * kBM : m_idx * kBM) + q * 32;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -301,7 +309,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // fp32 output: thread == row writes its 32 consecutive columns (one full 128-byte line)
           const int grow = row_base + lane;
           if (grow < p.M) {
-            float* orow = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(grow) * p.ldo + col0;
+            float* orow = reinterpret_cast<float*>(p.out) + (static_cast<int64_t>(ks) * p.M + grow) * p.ldo + col0;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               if (col0 + g * 4 < p.N) {
@@ -438,7 +446,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int workers = kPair ? sms / 2 : sms;
   const int grid = (tiles < workers ? tiles : workers) * (kPair ? 2 : 1);
   LLB_CUDA(launch_ex(gemm_bf16_kernel<BN, kFp8, kPair>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
@@ -468,7 +476,7 @@ static int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, con
 static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
                      int64_t ldo, int M, int N, int K, int epilogue, const void* bias, const void* gate,
                      int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
-                     const float* a_scale, const float* w_scale, void* stream) {
+                     const float* a_scale, const float* w_scale, void* stream, int k_splits = 1) {
   using namespace llb;
   LLB_CHECK_ARG(A && W && out, "gemm: null tensor");
   LLB_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -479,6 +487,13 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
                 "gemm_fp8: needs a_scale[M] and a 16-byte aligned w_scale[N]");
   LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_GELU_BF16, "gemm: unknown epilogue %d", epilogue);
   LLB_CHECK_ARG(epilogue != LLB_EPI_BIAS_F32 || ldo % 4 == 0, "gemm: fp32 output needs ldo %% 4 == 0");
+  {
+    const int nkb = (K + (fp8 ? 128 : kBK) - 1) / (fp8 ? 128 : kBK);
+    LLB_CHECK_ARG(k_splits >= 1 && k_splits <= nkb && (k_splits - 1) * ((nkb + k_splits - 1) / k_splits) < nkb,
+                  "gemm: k_splits=%d leaves an empty split for K=%d", k_splits, K);
+    LLB_CHECK_ARG(k_splits == 1 || (epilogue == LLB_EPI_BIAS_F32 && bias == nullptr),
+                  "gemm: split-K writes raw fp32 partials");
+  }
   if (epilogue == LLB_EPI_BIAS_GATE_RES) {
     LLB_CHECK_ARG(gate && res && rows_per_gate > 0 && ld_gate % 8 == 0 && ld_res % 8 == 0,
                   "gemm: gate/residual epilogue needs gate, res, rows_per_gate");
@@ -506,7 +521,7 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
       const int m_tiles = pr ? (M + 2 * kBM - 1) / (2 * kBM) : (M + kBM - 1) / kBM;
       for (int i = 0; i < 3; ++i) {
         const int cand = 128 + 64 * i;
-        const int tiles = m_tiles * ((N + cand - 1) / cand);
+        const int tiles = m_tiles * ((N + cand - 1) / cand) * k_splits;
         const int waves = (tiles + workers - 1) / workers;
         const double cost = waves * (fp8 ? kCostFp8[pr][i] : kCostBf16[pr][i]);
         if (cost < best) { best = cost; bn = cand; pair = pr != 0; }
@@ -535,6 +550,8 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   p.num_n_tiles = (N + bn - 1) / bn;
   p.a_scale = a_scale;
   p.w_scale = w_scale;
+  p.k_splits = k_splits;
+  p.kb_per_split = ((K + (fp8 ? 128 : kBK) - 1) / (fp8 ? 128 : kBK) + k_splits - 1) / k_splits;
 
   CUtensorMap ta, tb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -552,6 +569,71 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   rc = make_tmap_2d_bf16(&tb, W, N, K, ldw, b_box_rows, kBK);
   if (rc) return rc;
   return pair ? dispatch_bn<false, true>(bn, ta, tb, p, s) : dispatch_bn<false, false>(bn, ta, tb, p, s);
+}
+
+namespace llb {
+// out[m, n..n+7] = epilogue(sum over splits of ws[s][m][n..] + bias): the second half of a split-K GEMM.  Same rounding
+// points as the fused epilogues: y = bf16(acc + bias), then bf16(res + y).
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int k_splits, int M, int N, __nv_bfloat16* __restrict__ out,
+                     int64_t ldo, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* res, int64_t ld_res) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int nvec = N / 8;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(M) * nvec) return;
+  const int m = static_cast<int>(idx / nvec), n = static_cast<int>(idx % nvec) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < k_splits; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<int64_t>(s) * M + m) * N + n);
+    const float4 a = src[0], b = src[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  if (bias != nullptr) {
+    const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { acc[2 * e] += bf16_lo(bw[e]); acc[2 * e + 1] += bf16_hi(bw[e]); }
+  }
+  uint32_t o[4];
+  if (res != nullptr) {
+    const uint4 r4 = *reinterpret_cast<const uint4*>(res + static_cast<int64_t>(m) * ld_res + n);
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = pack_bf16x2(bf16_lo(rw[e]) + bf16_round(acc[2 * e]), bf16_hi(rw[e]) + bf16_round(acc[2 * e + 1]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(acc[2 * e], acc[2 * e + 1]);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<int64_t>(m) * ldo + n) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+}  // namespace llb
+
+extern "C" int llb_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
+                                    int M, int N, int K, int epilogue, const void* bias, const void* res,
+                                    int64_t ld_res, int k_splits, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
+  using namespace llb;
+  LLB_CHECK_ARG(epilogue == LLB_EPI_BIAS || epilogue == LLB_EPI_BIAS_RES, "gemm_splitk: epilogue %d unsupported", epilogue);
+  LLB_CHECK_ARG(out && workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && N % 8 == 0 && ldo % 8 == 0 &&
+                    workspace_bytes >= static_cast<int64_t>(k_splits) * M * N * 4,
+                "gemm_splitk: needs a 16-byte aligned workspace of k_splits * M * N floats");
+  LLB_CHECK_ARG((epilogue == LLB_EPI_BIAS_RES) == (res != nullptr) && ld_res % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(res) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "gemm_splitk: residual / alignment");
+  int rc = gemm_impl(false, A, lda, W, ldw, workspace, N, M, N, K, LLB_EPI_BIAS_F32, nullptr, nullptr, 0, 0, 0, nullptr,
+                     0, nullptr, nullptr, stream, k_splits);
+  if (rc) return rc;
+  const int64_t total = static_cast<int64_t>(M) * (N / 8);
+  LLB_CUDA(launch_ex(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), 1, true, static_cast<const float*>(workspace), k_splits, M, N,
+                     static_cast<__nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(bias),
+                     static_cast<const __nv_bfloat16*>(res), ld_res));
+  LLB_LAUNCH_CHECK("splitk_reduce_kernel");
+  return LLB_OK;
 }
 
 extern "C" int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* out,

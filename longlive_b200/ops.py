@@ -16,7 +16,7 @@ from ._lib import (EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI
                    EPI_BIAS_RES, EPI_BIAS_SILU, STEP_PARAMS_INT32, StepParams)
 
 __all__ = [
-    "gemm", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
+    "gemm", "gemm_splitk", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
     "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
     "build_rope_table", "launch_count",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES", "EPI_BIAS_F32",
@@ -68,6 +68,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         M, N, K, epilogue, _ptr(bias), _ptr(gate), gate.stride(0) if gate is not None else 0,
         rows_per_gate, gate_row0, _ptr(res), res.stride(0) if res is not None else 0, _stream())
     _lib.check(rc, "llb_gemm_bf16")
+    return out
+
+
+def gemm_splitk(a: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, k_splits: int,
+                bias: Optional[torch.Tensor] = None, *, res: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Split-K GEMM for skinny problems: out = (res +) a @ w^T (+ bias); workspace: float32, >= k_splits*M*N elements."""
+    _req(a, "a"); _req(w, "w"); _req(workspace, "workspace", torch.float32)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    _req(out, "out")
+    for t, n in ((bias, "bias"), (res, "res")):
+        if t is not None:
+            _req(t, n)
+    rc = _lib.lib().llb_gemm_bf16_splitk(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+        EPI_BIAS_RES if res is not None else EPI_BIAS, _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0,
+        k_splits, workspace.data_ptr(), workspace.numel() * 4, _stream())
+    _lib.check(rc, "llb_gemm_bf16_splitk")
     return out
 
 

@@ -13,7 +13,7 @@ as ~15 eager ops per block over all 512 padded positions.  Here one block is eig
     llb_rmsnorm                       norm1                                       (t5.py:57-62)
     llb_gemm_bf16  N = 3 * dim_attn   q | k | v fused, no bias                    (t5.py:92-94)
     llb_t5_attn                       bias + mask + softmax + PV per head         (t5.py:96-111)
-    llb_gemm_bf16  + BIAS_RES         o projection, x + y                         (t5.py:114, 166)
+    llb_gemm_bf16  + BIAS_RES         o projection, x + y (split-K for <= 256 rows) (t5.py:114, 166)
     llb_rmsnorm                       norm2
     llb_gemm_bf16  + BIAS_GELU_BF16   gelu(gate(x)), the reference's bf16 op chain (t5.py:46-50, 125)
     llb_gemm_bf16  + BIAS_MUL         fc1(x) * gelu(gate(x))                      (t5.py:133)
@@ -156,7 +156,10 @@ class UMT5Encoder(nn.Module):
             b = {"ids": z(B, self._rows_max(), dt=torch.int64), "lens": z(B, dt=torch.int32),
                  "x": z(B * Lp, self.dim), "xn": z(B * Lp, self.dim), "qkv": z(B * Lp, 3 * self.dim_attn),
                  "att": z(B * Lp, self.dim_attn), "g": z(B * Lp, self.dim_ffn), "h": z(B * Lp, self.dim_ffn),
-                 "out": z(B, self.text_len, self.dim)}
+                 "out": z(B, self.text_len, self.dim),
+                 # short prompts: the two N = dim projections have too few tiles to pull their weights through the
+                 # whole GPU, so their K range is split in two (fp32 partials, llb_gemm_bf16_splitk)
+                 "ws": z(2 * B * Lp * self.dim, dt=torch.float32) if B * Lp <= 256 else None}
             self._bufs = {key: b} if len(self._bufs) > 4 else {**self._bufs, key: b}
         return b
 
@@ -169,11 +172,17 @@ class UMT5Encoder(nn.Module):
             ops.rmsnorm(x, lw["n1"], self.eps, out=xn)
             ops.gemm(xn, lw["qkv"], out=qkv)
             ops.t5_attention(qkv, B, self.num_heads, b["lens"], lw["pos"], P["lut"], out=att)
-            ops.gemm(att, lw["o"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+            if b["ws"] is not None:
+                ops.gemm_splitk(att, lw["o"], b["ws"], 2, res=x, out=x)
+            else:
+                ops.gemm(att, lw["o"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
             ops.rmsnorm(x, lw["n2"], self.eps, out=xn)
             ops.gemm(xn, lw["gate"], epilogue=ops.EPI_BIAS_GELU_BF16, out=g)
             ops.gemm(xn, lw["fc1"], epilogue=ops.EPI_BIAS_MUL, res=g, out=h)
-            ops.gemm(h, lw["fc2"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+            if b["ws"] is not None:
+                ops.gemm_splitk(h, lw["fc2"], b["ws"], 2, res=x, out=x)
+            else:
+                ops.gemm(h, lw["fc2"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
         lens = b["lens"] if zero_padding else b["all_rows"]
         ops.t5_final_norm(x, P["norm"], B, rows_out, lens, self.eps, out=b["out"])
 

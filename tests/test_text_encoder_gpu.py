@@ -52,6 +52,26 @@ def test_gemm_mul_epilogue_and_no_bias():
         assert rel_l2(x, bf(x0.float() + bf(a.float() @ w.float().T).float())) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(256, 4096, 10240, 2), (128, 4096, 4096, 2), (200, 1032, 1000, 3), (256, 512, 192, 3)])
+def test_gemm_splitk(M, N, K, splits):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) * K ** -0.5).to(DEV)
+    bias = bf(torch.randn(N, generator=g)).to(DEV)
+    ws = torch.empty(splits * M * N, dtype=torch.float32, device=DEV)
+    ref = bf(a.float() @ w.float().T + bias.float())
+    out = ops.gemm_splitk(a, w, ws, splits, bias)
+    assert rel_l2(out, ref) < 4e-3
+    assert rel_l2(out, ops.gemm(a, w, bias)) < 3e-3            # same product, different fp32 summation order
+    x = bf(torch.randn(M, N, generator=g)).to(DEV)
+    x0 = x.clone()
+    ops.gemm_splitk(a, w, ws, splits, res=x, out=x)            # in-place residual, no bias
+    assert rel_l2(x, bf(x0.float() + bf(a.float() @ w.float().T).float())) < 4e-3
+    with pytest.raises(RuntimeError, match="empty split"):
+        ops.gemm_splitk(a[:, :128], w[:, :128], torch.empty(3 * M * N, dtype=torch.float32, device=DEV), 3)  # 2 k-blocks
+
+
 @pytest.mark.parametrize("C", [4096, 2056, 8192, 256])
 def test_rmsnorm_wide_rows(C):
     ops = _ops()

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--once", action="store_true",
                     help="one warm-up and one eager (no CUDA graph) encode of --tokens tokens, then exit: the run to "
                          "put under `ncu --metrics gpu__time_duration.sum` for a launch list")
+    ap.add_argument("--trim", action="store_true", help="with --once: compute only round_up(tokens, 128) rows")
     args = ap.parse_args()
     from longlive_b200 import synth
     from longlive_b200.text_encoder import UMT5Encoder
@@ -42,10 +43,10 @@ def main():
     if args.once:
         enc.use_cuda_graph = False
         ids, mask = to.synth_token_ids(cfg, 7, args.tokens, 1)
-        enc(ids, mask, trim_padding=False)
+        enc(ids, mask, trim_padding=args.trim)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        enc(ids, mask, trim_padding=False)
+        enc(ids, mask, trim_padding=args.trim)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
