@@ -310,7 +310,8 @@ int llb_vae_pixel_out(const void* in, float* out, int T, int64_t hw, int Cp, voi
 /* nn.Embedding lookup (t5.py:288): out[b * rows_per_seq + r, :] = table[ids[b * ld_ids + r], :], ids int64 */
 int llb_embed_rows(const void* table, int64_t vocab, const void* ids, int64_t ld_ids, void* out, int64_t ldo,
                    int batch, int rows_per_seq, int C, void* stream);
-/* T5Attention core (t5.py:96-111), head_dim 64, no 1/sqrt(d) scaling:
+/* T5Attention core (t5.py:96-111), head_dim 64, no 1/sqrt(d) scaling; tcgen05 kernel, rows_per_seq <= 512 (the
+ * logits of 128 query rows against 512 keys fill the 512 TMEM columns):
  *   qkv [batch * rows_per_seq, ld_qkv] = q | k | v column blocks of width n_heads * 64 (fused projection output)
  *   logits = bf16(bf16(q . k) + pos_emb[bucket_lut[key - query + lut_center]][head]); keys >= seq_lens[b] get
  *   probability 0 (reference: finfo.min fill); out = bf16(softmax_fp32(logits) V) -> [batch * rows_per_seq, ldo].

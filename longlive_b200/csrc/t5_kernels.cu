@@ -7,6 +7,7 @@
 // The wide-row RMS norm used by the blocks lives in row_kernels.cu (llb_rmsnorm, C > 2048 path).
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "llb_common.cuh"
 #include "llb_host.h"
@@ -94,237 +95,266 @@ t5_final_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bflo
 }
 
 // ------------------------------------------------------------------------------------------------
-// T5Attention core (t5.py:96-111) for head_dim 64:
+// T5Attention core (t5.py:96-111) for head_dim 64 on the 5th-generation tensor cores:
 //   logits = bf16(q . k)                      (einsum in bf16, fp32 accumulate; T5 does not scale)
 //   logits = bf16(logits + bias[h][key - query])    bias = per-block bucket table, buckets from a host LUT
 //   masked keys (key >= seq_len)  ->  probability exactly 0  (reference: finfo.min before the fp32 softmax)
-//   out = bf16(softmax_fp32(logits) V)
-// This is 2 % of the encoder's FLOPs (4.3 of 202 GFLOP per block at 512 tokens), sequence length <= 512 and
-// needs a per-element bias, so it is a register-level flash kernel on mma.sync.m16n8k16 rather than a TMEM
-// pipeline: one CTA = 128 query rows of one (batch, head), 8 warps x 16 rows; all keys / values of the head
-// are staged once in shared memory (row stride 144 B: conflict-free for both the 32-bit K fragment loads
-// and ldmatrix.trans on V).  Two passes over the keys, S recomputed in the second: pass 1 yields the fp32 row
-// maximum and denominator, pass 2 forms P = bf16(softmax) - the tensor the reference materialises - and O += P V,
-// so the rounding points are the reference's (an online softmax would round un-normalised probabilities).
+//   out = bf16(bf16(softmax_fp32(logits)) V)
+// (A register-level mma.sync.m16n8k16 version of this kernel was written first and ran at the same speed -
+// 32 us per launch at 512 rows, both are bound by the per-element softmax work of 128-256 threads per SM;
+// the tensor-core version below replaced it.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kT5D = 64;
-constexpr int kT5Stride = 72;
 
-struct T5AttnParams {
-  const __nv_bfloat16* qkv;  // [batch * rows_per_seq, ld]: q | k | v column blocks of width n_heads * 64
-  int64_t ld;
-  __nv_bfloat16* out;        // [batch * rows_per_seq, ldo]
-  int64_t ldo;
-  int rows_per_seq, n_heads;
-  int kv_cap;                     // shared-memory capacity in keys (multiple of 64, >= every valid length)
-  const int32_t* seq_lens;        // [batch] valid keys per sequence
-  const __nv_bfloat16* pos_emb;   // [num_buckets, n_heads]
-  const int32_t* bucket_lut;      // [2 * lut_center + 1]: bucket of (key - query) + lut_center
-  int lut_center;
-};
-
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
-                                                  uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(saddr));
-}
 __device__ __forceinline__ float ex2_ftz(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// bf16(a) + bf16(b) -> bf16, two lanes at once (add.rn.bf16x2: one rounding of the exact sum, which is what the
-// reference's bf16 tensor add yields)
-__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
 
-// kWarps x 16 query rows per CTA (8 warps = 128 rows, or 16 warps = 256 rows when that still fills the GPU:
-// the keys / values of the head are then staged once per 256 rows and a 512-token prompt is a single wave).
-template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32)
-t5_attn_kernel(const T5AttnParams p) {
-  constexpr int kThreads = kWarps * 32, kRows = kWarps * 16;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int Lp = p.rows_per_seq;
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* Vs = Ks + static_cast<size_t>(p.kv_cap) * kT5Stride;
-  // bias2[i] = (bias[i], bias[i + 1]) as bf16x2 for offset index i = key - query + Lp - 1: one aligned 32-bit
-  // read serves the two adjacent keys of an accumulator pair whatever the parity of i
-  uint32_t* bias2 = reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(p.kv_cap) * kT5Stride);  // [2 * Lp - 1]
+// ------------------------------------------------------------------------------------------------
+// 512 keys x fp32 is exactly the 512 TMEM columns of an SM,
+// so one CTA (128 query rows of one head) gets the WHOLE logit matrix of its rows in one go:
+//   TMA:   Q [128 x 64], K and V [kv x 64] of the head as 128-row SWIZZLE_128B boxes straight out of the fused
+//          q|k|v projection output (one tensor map, three column offsets)
+//   MMA 1: S = Q K^T                tcgen05.mma SS, 4 x (kv / 128) instructions, N = 128 each -> TMEM columns [0, kv)
+//   softmax warps (thread = row), three passes over TMEM, no recomputation:
+//          1  x = bf16(bf16(s) + bias), masked -> -inf, row max; x written back over s
+//          2  e = exp2((x - max) log2e), row sum;               e written back over x
+//          3  P = bf16(e / sum), packed two per column, written from column 0 upwards (chunk c of P lands in the
+//             columns of chunk c / 2 of e, which is already consumed)
+//   MMA 2: O = P V                  tcgen05.mma TS (P from TMEM, V as MN-major operand), kv / 16 instructions, N = 64,
+//          accumulator in columns [256, 320)
+// Rows of V at or beyond the prompt's length are zeroed in shared memory before MMA 2 (P = 0 there, but 0 x NaN
+// is NaN); masked K rows only produce logits that are replaced by -inf, never used in arithmetic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 160;  // 4 softmax warps (TMEM lane quadrants) + 1 TMA / MMA warp
+
+struct T5TcParams {
+  __nv_bfloat16* out;
+  int64_t ldo;
+  int rows_per_seq, n_heads, kv_cap;  // kv_cap: multiple of 128
+  const int32_t* seq_lens;
+  const __nv_bfloat16* pos_emb;
+  const int32_t* bucket_lut;
+  int lut_center;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+t5_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const T5TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // [0, 1024): barriers + TMEM slot; then Q (16 KB), K, V (kv_cap x 128 B each), bias table
+  const uint32_t bar_load = base, bar_s = base + 8, bar_p = base + 16, bar_o = base + 24, bar_v = base + 32;
+  const uint32_t tmem_slot = base + 64;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 64);
+  const uint32_t q_s = base + 1024;
+  const uint32_t k_s = q_s + 16384;
+  const uint32_t v_s = k_s + static_cast<uint32_t>(p.kv_cap) * 128u;
+  uint8_t* v_gen = gen + 1024 + 16384 + static_cast<size_t>(p.kv_cap) * 128;
+  float* sbias = reinterpret_cast<float*>(v_gen + static_cast<size_t>(p.kv_cap) * 128);  // [2 * Lp - 1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int width = p.n_heads * kT5D;
+  const int Lp = p.rows_per_seq;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int64_t seq_row0 = static_cast<int64_t>(b) * Lp;
-  const int row_cta = blockIdx.x * kRows;
-  const int row_w = row_cta + warp * 16;  // first query row of this warp (within the sequence)
-
   int kv_len = p.seq_lens[b];
   kv_len = kv_len < 0 ? 0 : (kv_len > p.kv_cap ? p.kv_cap : kv_len);
-  const int kv_pad = (kv_len + 63) & ~63;  // <= kv_cap (a multiple of 64)
-
-  if (kv_len == 0) {  // nothing to attend: the reference would produce a uniform average; rows are zeroed later anyway
-    for (int i = tid; i < kRows * (kT5D / 8); i += kThreads) {
-      const int r = i / (kT5D / 8), c = i % (kT5D / 8);
-      *reinterpret_cast<uint4*>(p.out + (seq_row0 + row_cta + r) * p.ldo + h * kT5D + c * 8) = make_uint4(0, 0, 0, 0);
-    }
+  if (kv_len == 0) {  // nothing to attend (rows are zeroed downstream anyway)
+    for (int i = tid; i < 128 * 8; i += kTcThreads)
+      *reinterpret_cast<uint4*>(p.out + (seq_row0 + qb * 128 + (i >> 3)) * p.ldo + h * kT5D + (i & 7) * 8) =
+          make_uint4(0, 0, 0, 0);
     return;
   }
+  const int kv_tiles = (kv_len + 127) >> 7;
 
-  // ---- stage K, V (rows of masked keys zeroed: 0 * garbage must stay 0) and this head's bias pairs
-  {
-    const __nv_bfloat16* kbase = p.qkv + seq_row0 * p.ld + width + h * kT5D;
-    const __nv_bfloat16* vbase = kbase + width;
-    for (int i = tid; i < kv_pad * (kT5D / 8); i += kThreads) {
-      const int key = i >> 3, c = i & 7;
-      uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (key < kv_len) {
-        kk = *reinterpret_cast<const uint4*>(kbase + static_cast<int64_t>(key) * p.ld + c * 8);
-        vv = *reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(key) * p.ld + c * 8);
-      }
-      *reinterpret_cast<uint4*>(Ks + key * kT5Stride + c * 8) = kk;
-      *reinterpret_cast<uint4*>(Vs + key * kT5Stride + c * 8) = vv;
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 4);
+      mbar_init(bar_o, 1);
+      mbar_init(bar_v, 4);
+      fence_barrier_init();
     }
-    const unsigned short* emb = reinterpret_cast<const unsigned short*>(p.pos_emb);
-    for (int i = tid; i < 2 * Lp - 1; i += kThreads) {
-      const int d = i - (Lp - 1) + p.lut_center;
-      const uint32_t lo = emb[p.bucket_lut[d] * p.n_heads + h];
-      const uint32_t hi = i + 1 < 2 * Lp - 1 ? emb[p.bucket_lut[d + 1] * p.n_heads + h] : 0u;
-      bias2[i] = lo | (hi << 16);
-    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
   }
-
-  // ---- Q fragments straight from global memory (A operand, row-major 16 x 16 per k-chunk)
-  uint32_t qa[4][4];
-  {
-    const __nv_bfloat16* q0 = p.qkv + (seq_row0 + row_w + g) * p.ld + h * kT5D + 2 * t;
-    const __nv_bfloat16* q1 = q0 + 8 * p.ld;
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
-      qa[kc][0] = *reinterpret_cast<const uint32_t*>(q0 + kc * 16);
-      qa[kc][1] = *reinterpret_cast<const uint32_t*>(q1 + kc * 16);
-      qa[kc][2] = *reinterpret_cast<const uint32_t*>(q0 + kc * 16 + 8);
-      qa[kc][3] = *reinterpret_cast<const uint32_t*>(q1 + kc * 16 + 8);
-    }
-  }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
 
-  constexpr float kLog2e = 1.4426950408889634f;
-  // S block (16 query rows x 64 keys per warp): bf16(bf16(q . k) + bias) as two packed roundings, keys beyond the
-  // prompt's length set to -inf (only the block that straddles kv_len needs the comparison)
-  const uint32_t* bias_r0 = bias2 + (2 * t - (row_w + g) + Lp - 1);  // + key column base; row g
-  const uint32_t* bias_r1 = bias_r0 - 8;                              // row g + 8
-  auto logits_block = [&](int kb, float (&s)[8][4]) {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      const __nv_bfloat16* krow = Ks + (kb + nt * 8 + g) * kT5Stride + 2 * t;
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + kc * 16);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + kc * 16 + 8);
-        mma_bf16_16816(s[nt], qa[kc], b0, b1);
-      }
-      const uint32_t x0 = add_bf16x2(pack_bf16x2(s[nt][0], s[nt][1]), bias_r0[kb + nt * 8]);
-      const uint32_t x1 = add_bf16x2(pack_bf16x2(s[nt][2], s[nt][3]), bias_r1[kb + nt * 8]);
-      s[nt][0] = bf16_lo(x0); s[nt][1] = bf16_hi(x0);
-      s[nt][2] = bf16_lo(x1); s[nt][3] = bf16_hi(x1);
-    }
-    if (kb + 64 > kv_len) {  // warp-uniform
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = kb + nt * 8 + 2 * t;
-        if (col >= kv_len) s[nt][0] = s[nt][2] = -CUDART_INF_F;
-        if (col + 1 >= kv_len) s[nt][1] = s[nt][3] = -CUDART_INF_F;
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA + MMA issue (whole warp, one lane acts)
+    const int width = p.n_heads * kT5D;
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_load, static_cast<uint32_t>(1 + 2 * kv_tiles) * 16384u);
+      tma_load_2d(q_s, &tmap, bar_load, h * kT5D, static_cast<int>(seq_row0) + qb * 128);
+      for (int i = 0; i < kv_tiles; ++i) {
+        tma_load_2d(k_s + i * 16384, &tmap, bar_load, width + h * kT5D, static_cast<int>(seq_row0) + i * 128);
+        tma_load_2d(v_s + i * 16384, &tmap, bar_load, 2 * width + h * kT5D, static_cast<int>(seq_row0) + i * 128);
       }
     }
-  };
+    __syncwarp();
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kT5D, 0, 1);
+    if (elect_one()) {
+      for (int i = 0; i < kv_tiles; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // head dim 64 = 4 x K16; +32 bytes inside the 128-byte swizzle row
+          umma_ss(tmem_base + i * 128, umma_desc_kmajor(q_s + k * 32), umma_desc_kmajor(k_s + i * 16384 + k * 32),
+                  idesc_qk, k != 0);
+      }
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_v, 0);  // V tail rows zeroed (generic-proxy writes fenced by the writers)
+    mbar_wait(bar_p, 0);  // P complete in TMEM
+    tc_fence_after();
+    if (elect_one()) {
+      for (int kk = 0; kk < kv_tiles * 8; ++kk)  // 16 keys per instruction
+        umma_ts(tmem_base + 256, tmem_base + kk * 8, umma_desc_mnmajor(v_s + kk * 2048, 16384), idesc_pv, kk != 0);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax / epilogue warps, thread = query row
+    const int row = qb * 128 + warp * 32 + lane;  // within the sequence
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    {
+      const unsigned short* emb = reinterpret_cast<const unsigned short*>(p.pos_emb);
+      for (int i = tid; i < 2 * Lp - 1; i += 128) {
+        const uint32_t bits = emb[p.bucket_lut[i - (Lp - 1) + p.lut_center] * p.n_heads + h];
+        sbias[i] = __uint_as_float(bits << 16);
+      }
+    }
+    mbar_wait(bar_load, 0);
+    {
+      const int r = kv_len + tid;  // one row per thread covers the at most 127 tail rows of the last box
+      if (r < kv_tiles * 128) {
+        uint4* vr = reinterpret_cast<uint4*>(v_gen + static_cast<size_t>(r) * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vr[i] = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_smem();
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // bias table complete
+    if (lane == 0) mbar_arrive(bar_v);
+    const float* brow = sbias + (Lp - 1 - row);  // + key column
+    constexpr float kLog2e = 1.4426950408889634f;
+    const int nchunks = kv_tiles * 4;
 
-  // ---- pass 1: row maximum and softmax denominator (fp32, like F.softmax(attn.float()))
-  float m_run[2] = {-CUDART_INF_F, -CUDART_INF_F};
-  float l_run[2] = {0.f, 0.f};
-  for (int kb = 0; kb < kv_pad; kb += 64) {
-    float s[8][4];
-    logits_block(kb, s);
-    float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    // Every pass streams the row through two register buffers: the tcgen05.ld of the next 32-column chunk is in
+    // flight while the current one is processed (one warp per scheduler, nothing else hides that latency).
+    uint32_t va[32], vb[32];
+    // pass 1: logits with bias and mask, the reference's two bf16 roundings, row max
+    float m = -CUDART_INF_F;
+    auto pass1 = [&](uint32_t (&v)[32], int c) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
-      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+      for (int i = 0; i < 32; ++i) {
+        const int col = c * 32 + i;
+        float x = bf16_round(bf16_round(__uint_as_float(v[i])) + brow[col]);
+        x = col < kv_len ? x : -CUDART_INF_F;
+        m = fmaxf(m, x);
+        v[i] = __float_as_uint(x);
+      }
+      tmem_st32(t_row + c * 32, v);
+    };
+    tmem_ld32(t_row, va);
+    tmem_wait_ld();
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c += 2) {  // nchunks is a multiple of 4
+      tmem_ld32(t_row + (c + 1) * 32, vb);
+      pass1(va, c);
+      tmem_wait_ld();
+      if (c + 2 < nchunks) tmem_ld32(t_row + (c + 2) * 32, va);
+      pass1(vb, c + 1);
+      tmem_wait_ld();
     }
-    float mneg[2];
+    tmem_wait_st();
+    // pass 2: exponentials (fp32, like F.softmax(attn.float())) and the row sum
+    const float mneg = -m * kLog2e;
+    float l = 0.f;
+    auto pass2 = [&](uint32_t (&v)[32], int c) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);  // finite from the first block on (key 0 is never masked)
-      l_run[r] *= ex2_ftz((m_run[r] - m_new) * kLog2e);
-      m_run[r] = m_new;
-      mneg[r] = -m_new * kLog2e;
+      for (int i = 0; i < 32; ++i) {
+        const float e = ex2_ftz(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+        l += e;
+        v[i] = __float_as_uint(e);
+      }
+      tmem_st32(t_row + c * 32, v);
+    };
+    tmem_ld32(t_row, va);
+    tmem_wait_ld();
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c += 2) {
+      tmem_ld32(t_row + (c + 1) * 32, vb);
+      pass2(va, c);
+      tmem_wait_ld();
+      if (c + 2 < nchunks) tmem_ld32(t_row + (c + 2) * 32, va);
+      pass2(vb, c + 1);
+      tmem_wait_ld();
     }
+    tmem_wait_st();
+    // pass 3: P = bf16(softmax), two keys per column, compacted to columns [0, kv / 2): chunk c lands in the columns
+    // of chunk c / 2, which is consumed (the chunk in flight is c + 1)
+    const float inv = 1.f / l;
+    auto pass3 = [&](const uint32_t (&v)[32], int c) {
+      uint32_t pk[16];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      l_run[0] += ex2_ftz(fmaf(s[nt][0], kLog2e, mneg[0])) + ex2_ftz(fmaf(s[nt][1], kLog2e, mneg[0]));
-      l_run[1] += ex2_ftz(fmaf(s[nt][2], kLog2e, mneg[1])) + ex2_ftz(fmaf(s[nt][3], kLog2e, mneg[1]));
+      for (int i = 0; i < 16; ++i)
+        pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
+      tmem_st16(t_row + c * 16, pk);
+    };
+    tmem_ld32(t_row, va);
+    tmem_wait_ld();
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c += 2) {
+      tmem_ld32(t_row + (c + 1) * 32, vb);
+      pass3(va, c);
+      tmem_wait_ld();
+      if (c + 2 < nchunks) tmem_ld32(t_row + (c + 2) * 32, va);
+      pass3(vb, c + 1);
+      tmem_wait_ld();
     }
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
-    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
-  }
-  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
-  const float mneg0 = -m_run[0] * kLog2e, mneg1 = -m_run[1] * kLog2e;
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
 
-  // ---- pass 2: P = bf16(softmax) exactly as the reference materialises it (.type_as(attn)), O += P V
-  float o[8][4];
+    // epilogue: O [128 x 64] fp32 -> bf16 -> out
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.out + (seq_row0 + row) * p.ldo + h * kT5D;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  // ldmatrix.x4.trans lane address inside a 16-key x 16-dim V block: matrices (keys 0-7 | 8-15) x (dims 0-7 | 8-15)
-  const uint32_t v_lane = smem_u32(Vs) + static_cast<uint32_t>(((lane & 7) + ((lane >> 3) & 1) * 8) * kT5Stride +
-                                                               (lane >> 4) * 8) * 2u;
-  for (int kb = 0; kb < kv_pad; kb += 64) {
-    float s[8][4];
-    logits_block(kb, s);
-    uint32_t pa[4][4];
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_row + 256 + c * 32, v);
+      tmem_wait_ld();
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = ex2_ftz(fmaf(s[nt][0], kLog2e, mneg0)) * inv0, p1 = ex2_ftz(fmaf(s[nt][1], kLog2e, mneg0)) * inv0;
-      const float p2 = ex2_ftz(fmaf(s[nt][2], kLog2e, mneg1)) * inv1, p3 = ex2_ftz(fmaf(s[nt][3], kLog2e, mneg1)) * inv1;
-      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-    }
-    // k index = key (16 per chunk), n index = head dim (8 per tile, two tiles per ldmatrix.x4)
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t r0, r1, r2, r3;
-        ldmatrix_x4_trans(v_lane + static_cast<uint32_t>((kb + kc * 16) * kT5Stride + dp * 16) * 2u, r0, r1, r2, r3);
-        mma_bf16_16816(o[2 * dp], pa[kc], r0, r1);
-        mma_bf16_16816(o[2 * dp + 1], pa[kc], r2, r3);
+      for (int i = 0; i < 4; ++i) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+        w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+        w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+        w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+        *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
       }
     }
   }
-
-  // ---- store (P was normalised before the product, as in the reference)
-  __nv_bfloat16* o0 = p.out + (seq_row0 + row_w + g) * p.ldo + h * kT5D + 2 * t;
-  __nv_bfloat16* o1 = o0 + 8 * p.ldo;
-#pragma unroll
-  for (int dt = 0; dt < 8; ++dt) {
-    *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16x2(o[dt][0], o[dt][1]);
-    *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16x2(o[dt][2], o[dt][3]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -363,37 +393,37 @@ extern "C" int llb_t5_attn(const void* qkv, int64_t ld_qkv, void* out, int64_t l
   using namespace llb;
   LLB_CHECK_ARG(qkv && out && seq_lens_dev && pos_emb && bucket_lut_dev && batch > 0 && n_heads > 0,
                 "t5_attn: null tensor / bad shape");
-  LLB_CHECK_ARG(rows_per_seq > 0 && rows_per_seq % 128 == 0 && rows_per_seq <= 1024,
-                "t5_attn: rows_per_seq=%d must be a multiple of 128 (<= 1024)", rows_per_seq);
+  LLB_CHECK_ARG(rows_per_seq > 0 && rows_per_seq % 128 == 0 && rows_per_seq <= 512,
+                "t5_attn: rows_per_seq=%d must be a multiple of 128 (<= 512: the logits of a row fill TMEM)", rows_per_seq);
   LLB_CHECK_ARG(lut_center >= rows_per_seq - 1, "t5_attn: bucket LUT too short for %d rows", rows_per_seq);
   LLB_CHECK_ARG(ld_qkv % 8 == 0 && ldo % 8 == 0 && ld_qkv >= 3 * n_heads * kT5D && ldo >= n_heads * kT5D,
                 "t5_attn: leading dimensions");
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "t5_attn: 16-byte alignment");
-  // shared memory holds the valid keys only (max_seq_len: host-known upper bound of seq_lens, <= 0 = rows_per_seq)
-  int kv_cap = max_seq_len > 0 && max_seq_len < rows_per_seq ? max_seq_len : rows_per_seq;
-  kv_cap = (kv_cap + 63) & ~63;
-  const size_t smem = static_cast<size_t>(kv_cap) * kT5Stride * 2 * 2 + (2 * rows_per_seq - 1) * sizeof(uint32_t);
-  LLB_CHECK_ARG(smem <= 227 * 1024, "t5_attn: %d keys do not fit shared memory", kv_cap);
-  // 256-row CTAs when they still cover most of the GPU in one wave, else 128-row CTAs
-  const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
-  const bool wide = rows_per_seq % 256 == 0 && (rows_per_seq / 256) * n_heads * batch >= (sms * 3) / 4;
-  static size_t attr_smem[2] = {0, 0};
-  if (smem > attr_smem[wide]) {
-    if (wide) LLB_CUDA(cudaFuncSetAttribute(t5_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    else LLB_CUDA(cudaFuncSetAttribute(t5_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem[wide] = smem;
+  // the logits of 128 query rows against up to 512 keys fill the 512 TMEM columns exactly; shared memory holds the
+  // valid keys only (max_seq_len: host-known upper bound of seq_lens, <= 0 = rows_per_seq)
+  {
+    int cap = max_seq_len > 0 && max_seq_len < rows_per_seq ? max_seq_len : rows_per_seq;
+    cap = (cap + 127) & ~127;
+    const size_t smem_tc = 1024 + 1024 + 16384 + static_cast<size_t>(cap) * 256 + (2 * rows_per_seq - 1) * sizeof(float);
+    static size_t attr_tc = 0;
+    if (smem_tc > attr_tc) {
+      LLB_CUDA(cudaFuncSetAttribute(t5_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_tc)));
+      attr_tc = smem_tc;
+    }
+    CUtensorMap tm;
+    int rc = make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(batch) * rows_per_seq, static_cast<uint64_t>(3) * n_heads * kT5D,
+                               ld_qkv, 128, 64);
+    if (rc) return rc;
+    T5TcParams tp;
+    tp.out = static_cast<__nv_bfloat16*>(out); tp.ldo = ldo;
+    tp.rows_per_seq = rows_per_seq; tp.n_heads = n_heads; tp.kv_cap = cap;
+    tp.seq_lens = seq_lens_dev;
+    tp.pos_emb = static_cast<const __nv_bfloat16*>(pos_emb);
+    tp.bucket_lut = bucket_lut_dev; tp.lut_center = lut_center;
+    t5_attn_tc_kernel<<<dim3(rows_per_seq / 128, n_heads, batch), kTcThreads, smem_tc, static_cast<cudaStream_t>(stream)>>>(tm, tp);
+    LLB_LAUNCH_CHECK("t5_attn_tc_kernel");
+    return LLB_OK;
   }
-  T5AttnParams p;
-  p.qkv = static_cast<const __nv_bfloat16*>(qkv); p.ld = ld_qkv;
-  p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
-  p.rows_per_seq = rows_per_seq; p.n_heads = n_heads; p.kv_cap = kv_cap;
-  p.seq_lens = seq_lens_dev;
-  p.pos_emb = static_cast<const __nv_bfloat16*>(pos_emb);
-  p.bucket_lut = bucket_lut_dev; p.lut_center = lut_center;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wide) t5_attn_kernel<16><<<dim3(rows_per_seq / 256, n_heads, batch), 512, smem, st>>>(p);
-  else t5_attn_kernel<8><<<dim3(rows_per_seq / 128, n_heads, batch), 256, smem, st>>>(p);
-  LLB_LAUNCH_CHECK("t5_attn_kernel");
-  return LLB_OK;
 }
+

@@ -12,7 +12,7 @@ as ~15 eager ops per block over all 512 padded positions.  Here one block is eig
 
     llb_rmsnorm                       norm1                                       (t5.py:57-62)
     llb_gemm_bf16  N = 3 * dim_attn   q | k | v fused, no bias                    (t5.py:92-94)
-    llb_t5_attn                       bias + mask + softmax + PV per head         (t5.py:96-111)
+    llb_t5_attn                       bias + mask + softmax + PV per head, tcgen05 (t5.py:96-111)
     llb_gemm_bf16  + BIAS_RES         o projection, x + y (split-K for <= 256 rows) (t5.py:114, 166)
     llb_rmsnorm                       norm2
     llb_gemm_bf16  + BIAS_GELU_BF16   gelu(gate(x)), the reference's bf16 op chain (t5.py:46-50, 125)
