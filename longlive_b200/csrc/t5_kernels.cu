@@ -111,6 +111,13 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// bf16(a) + bf16(b) -> bf16, two lanes at once (add.rn.bf16x2: one rounding of the exact sum, which is what the
+// reference's bf16 tensor add yields)
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // 512 keys x fp32 is exactly the 512 TMEM columns of an SM,
@@ -153,7 +160,9 @@ t5_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const T5TcParams p) 
   const uint32_t k_s = q_s + 16384;
   const uint32_t v_s = k_s + static_cast<uint32_t>(p.kv_cap) * 128u;
   uint8_t* v_gen = gen + 1024 + 16384 + static_cast<size_t>(p.kv_cap) * 128;
-  float* sbias = reinterpret_cast<float*>(v_gen + static_cast<size_t>(p.kv_cap) * 128);  // [2 * Lp - 1]
+  // bias2[i] = (bias[i], bias[i + 1]) as bf16x2 for offset index i = key - query + Lp - 1: one aligned 32-bit read
+  // serves two adjacent keys whatever the parity of i
+  uint32_t* bias2 = reinterpret_cast<uint32_t*>(v_gen + static_cast<size_t>(p.kv_cap) * 128);  // [2 * Lp - 1]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Lp = p.rows_per_seq;
@@ -230,8 +239,10 @@ t5_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const T5TcParams p) 
     {
       const unsigned short* emb = reinterpret_cast<const unsigned short*>(p.pos_emb);
       for (int i = tid; i < 2 * Lp - 1; i += 128) {
-        const uint32_t bits = emb[p.bucket_lut[i - (Lp - 1) + p.lut_center] * p.n_heads + h];
-        sbias[i] = __uint_as_float(bits << 16);
+        const int d = i - (Lp - 1) + p.lut_center;
+        const uint32_t lo = emb[p.bucket_lut[d] * p.n_heads + h];
+        const uint32_t hi = i + 1 < 2 * Lp - 1 ? emb[p.bucket_lut[d + 1] * p.n_heads + h] : 0u;
+        bias2[i] = lo | (hi << 16);
       }
     }
     mbar_wait(bar_load, 0);
@@ -246,7 +257,7 @@ t5_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const T5TcParams p) 
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // bias table complete
     if (lane == 0) mbar_arrive(bar_v);
-    const float* brow = sbias + (Lp - 1 - row);  // + key column
+    const uint32_t* brow = bias2 + (Lp - 1 - row);  // + (even) key column
     constexpr float kLog2e = 1.4426950408889634f;
     const int nchunks = kv_tiles * 4;
 
@@ -259,13 +270,19 @@ t5_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap, const T5TcParams p) 
     float m = -CUDART_INF_F;
     auto pass1 = [&](uint32_t (&v)[32], int c) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = c * 32 + i;
-        float x = bf16_round(bf16_round(__uint_as_float(v[i])) + brow[col]);
-        x = col < kv_len ? x : -CUDART_INF_F;
-        m = fmaxf(m, x);
-        v[i] = __float_as_uint(x);
+      for (int i = 0; i < 16; ++i) {  // two keys at a time: cvt.rn.bf16x2, add.rn.bf16x2 against the paired bias
+        const uint32_t x2 = add_bf16x2(pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                       brow[c * 32 + 2 * i]);
+        v[2 * i] = x2 << 16;
+        v[2 * i + 1] = x2 & 0xffff0000u;
       }
+      if (c * 32 + 32 > kv_len) {  // only the chunk that straddles the prompt length (and those beyond it)
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i >= kv_len) v[i] = 0xff800000u;  // -inf
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
       tmem_st32(t_row + c * 32, v);
     };
     tmem_ld32(t_row, va);
