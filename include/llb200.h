@@ -157,10 +157,13 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
 /* Split-K form for skinny problems (the umT5 encoder's N = 4096 projections at 128-256 token rows stream 33-84 MB of
  * weights through only 64 CTAs otherwise): k_splits partial products are written as fp32 to `workspace`
  * (k_splits * M * N floats, caller-owned) and a second launch sums them and applies the epilogue
- * (LLB_EPI_BIAS or LLB_EPI_BIAS_RES; `res` may alias `out`). */
+ * (LLB_EPI_BIAS or LLB_EPI_BIAS_RES; `res` may alias `out`).  With norm_out != NULL (N <= 8192) the second launch also
+ * writes norm_out = bf16(bf16(out * rsqrt(mean(out^2) + norm_eps)) * norm_w): the T5LayerNorm that follows the projection
+ * (wan/modules/t5.py:57-62, 166-167). */
 int llb_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo, int M,
                          int N, int K, int epilogue, const void* bias, const void* res, int64_t ld_res,
-                         int k_splits, void* workspace, int64_t workspace_bytes, void* stream);
+                         int k_splits, void* workspace, int64_t workspace_bytes, const void* norm_w,
+                         void* norm_out, int64_t ld_norm, float norm_eps, void* stream);
 
 /* Optional FP8 linears (README.md:50 of the reference advertises "FP8 quantization" at 24.8 FPS but
  * ships no code for it, reports.md:24,39).  W8A8 with e4m3 operands on tcgen05 kind::f8f6f4:

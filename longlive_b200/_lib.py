@@ -129,7 +129,8 @@ _PROTOS = {
     "llb_gemm_bf16_splitk": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
-         C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
+         C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+         C.c_float, C.c_void_p],
     ),
     "llb_gemm_fp8": (
         C.c_int,

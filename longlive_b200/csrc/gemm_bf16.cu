@@ -609,11 +609,86 @@ splitk_reduce_kernel(const float* __restrict__ ws, int k_splits, int M, int N, _
   }
   *reinterpret_cast<uint4*>(out + static_cast<int64_t>(m) * ldo + n) = make_uint4(o[0], o[1], o[2], o[3]);
 }
+// Row-per-CTA form of the reduction that also applies the RMS norm that follows the projection (T5LayerNorm /
+// WanRMSNorm arithmetic: bf16(bf16(x * rstd) * w), statistics over the bf16-rounded x): x goes to `out`, the
+// normalised row to `norm_out`, and the separate norm launch disappears.  N <= 256 * 4 * 8 = 8192.
+__global__ void __launch_bounds__(256)
+splitk_reduce_norm_kernel(const float* __restrict__ ws, int k_splits, int M, int N, __nv_bfloat16* __restrict__ out,
+                          int64_t ldo, const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* res, int64_t ld_res,
+                          const __nv_bfloat16* __restrict__ norm_w, __nv_bfloat16* __restrict__ norm_out,
+                          int64_t ld_norm, float eps) {
+  __shared__ float red[8];
+  griddep_wait();
+  griddep_launch_dependents();
+  const int m = blockIdx.x;
+  const int nvec = N / 8;
+  uint4 xv[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      const int n = vi * 8;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < k_splits; ++s) {
+        const float4* src = reinterpret_cast<const float4*>(ws + (static_cast<int64_t>(s) * M + m) * N + n);
+        const float4 a = src[0], b = src[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+      if (bias != nullptr) {
+        const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[2 * e] += bf16_lo(bw[e]); acc[2 * e + 1] += bf16_hi(bw[e]); }
+      }
+      uint32_t o[4];
+      if (res != nullptr) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(res + static_cast<int64_t>(m) * ld_res + n);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          o[e] = pack_bf16x2(bf16_lo(rw[e]) + bf16_round(acc[2 * e]), bf16_hi(rw[e]) + bf16_round(acc[2 * e + 1]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(acc[2 * e], acc[2 * e + 1]);
+      }
+      xv[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(m) * ldo + n) = xv[i];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss += bf16_lo(o[e]) * bf16_lo(o[e]) + bf16_hi(o[e]) * bf16_hi(o[e]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / static_cast<float>(N) + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&xv[i]);
+      const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(norm_w) + vi);
+      const uint32_t* g = reinterpret_cast<const uint32_t*>(&g4);
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        o[e] = pack_bf16x2(bf16_round(bf16_lo(w[e]) * rstd) * bf16_lo(g[e]),
+                           bf16_round(bf16_hi(w[e]) * rstd) * bf16_hi(g[e]));
+      *reinterpret_cast<uint4*>(norm_out + static_cast<int64_t>(m) * ld_norm + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
 }  // namespace llb
 
 extern "C" int llb_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, int64_t ldw, void* out, int64_t ldo,
                                     int M, int N, int K, int epilogue, const void* bias, const void* res,
                                     int64_t ld_res, int k_splits, void* workspace, int64_t workspace_bytes,
+                                    const void* norm_w, void* norm_out, int64_t ld_norm, float norm_eps,
                                     void* stream) {
   using namespace llb;
   LLB_CHECK_ARG(epilogue == LLB_EPI_BIAS || epilogue == LLB_EPI_BIAS_RES, "gemm_splitk: epilogue %d unsupported", epilogue);
@@ -627,6 +702,18 @@ extern "C" int llb_gemm_bf16_splitk(const void* A, int64_t lda, const void* W, i
   int rc = gemm_impl(false, A, lda, W, ldw, workspace, N, M, N, K, LLB_EPI_BIAS_F32, nullptr, nullptr, 0, 0, 0, nullptr,
                      0, nullptr, nullptr, stream, k_splits);
   if (rc) return rc;
+  if (norm_out != nullptr) {
+    LLB_CHECK_ARG(norm_w != nullptr && N <= 8192 && ld_norm % 8 == 0 && (reinterpret_cast<uintptr_t>(norm_out) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(norm_w) & 15) == 0,
+                  "gemm_splitk: fused norm needs norm_w, N <= 8192 and 16-byte aligned rows");
+    LLB_CUDA(launch_ex(splitk_reduce_norm_kernel, dim3(static_cast<unsigned>(M)), dim3(256), 0,
+                       static_cast<cudaStream_t>(stream), 1, true, static_cast<const float*>(workspace), k_splits, M, N,
+                       static_cast<__nv_bfloat16*>(out), ldo, static_cast<const __nv_bfloat16*>(bias),
+                       static_cast<const __nv_bfloat16*>(res), ld_res, static_cast<const __nv_bfloat16*>(norm_w),
+                       static_cast<__nv_bfloat16*>(norm_out), ld_norm, norm_eps));
+    LLB_LAUNCH_CHECK("splitk_reduce_norm_kernel");
+    return LLB_OK;
+  }
   const int64_t total = static_cast<int64_t>(M) * (N / 8);
   LLB_CUDA(launch_ex(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
                      static_cast<cudaStream_t>(stream), 1, true, static_cast<const float*>(workspace), k_splits, M, N,

@@ -73,8 +73,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 
 def gemm_splitk(a: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, k_splits: int,
                 bias: Optional[torch.Tensor] = None, *, res: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Split-K GEMM for skinny problems: out = (res +) a @ w^T (+ bias); workspace: float32, >= k_splits*M*N elements."""
+                out: Optional[torch.Tensor] = None, norm_w: Optional[torch.Tensor] = None,
+                norm_out: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
+    """Split-K GEMM for skinny problems: out = (res +) a @ w^T (+ bias); workspace: float32, >= k_splits*M*N elements.
+    With norm_w / norm_out the reduce launch also writes the RMS norm of the result rows into norm_out."""
     _req(a, "a"); _req(w, "w"); _req(workspace, "workspace", torch.float32)
     M, K = a.shape
     N = w.shape[0]
@@ -87,7 +89,8 @@ def gemm_splitk(a: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, k_spl
     rc = _lib.lib().llb_gemm_bf16_splitk(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), M, N, K,
         EPI_BIAS_RES if res is not None else EPI_BIAS, _ptr(bias), _ptr(res), res.stride(0) if res is not None else 0,
-        k_splits, workspace.data_ptr(), workspace.numel() * 4, _stream())
+        k_splits, workspace.data_ptr(), workspace.numel() * 4, _ptr(norm_w) if norm_out is not None else None,
+        _ptr(norm_out), norm_out.stride(0) if norm_out is not None else 0, C.c_float(norm_eps), _stream())
     _lib.check(rc, "llb_gemm_bf16_splitk")
     return out
 

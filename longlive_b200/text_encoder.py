@@ -168,19 +168,26 @@ class UMT5Encoder(nn.Module):
         P = self._packed
         x, xn, qkv, att, g, h = b["x"], b["xn"], b["qkv"], b["att"], b["g"], b["h"]
         ops.embed_rows(P["emb"], b["ids"], Lp, out=x)
-        for lw in P["layers"]:
-            ops.rmsnorm(x, lw["n1"], self.eps, out=xn)
+        ws = b["ws"]
+        layers = P["layers"]
+        normed = False  # xn already holds norm1(x) of the coming block (written by the previous block's fc2 reduce)
+        for i, lw in enumerate(layers):
+            if not normed:
+                ops.rmsnorm(x, lw["n1"], self.eps, out=xn)
             ops.gemm(xn, lw["qkv"], out=qkv)
             ops.t5_attention(qkv, B, self.num_heads, b["lens"], lw["pos"], P["lut"], out=att)
-            if b["ws"] is not None:
-                ops.gemm_splitk(att, lw["o"], b["ws"], 2, res=x, out=x)
+            if ws is not None:  # split-K; its reduce launch also applies norm2
+                ops.gemm_splitk(att, lw["o"], ws, 2, res=x, out=x, norm_w=lw["n2"], norm_out=xn, norm_eps=self.eps)
             else:
                 ops.gemm(att, lw["o"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
-            ops.rmsnorm(x, lw["n2"], self.eps, out=xn)
+                ops.rmsnorm(x, lw["n2"], self.eps, out=xn)
             ops.gemm(xn, lw["gate"], epilogue=ops.EPI_BIAS_GELU_BF16, out=g)
             ops.gemm(xn, lw["fc1"], epilogue=ops.EPI_BIAS_MUL, res=g, out=h)
-            if b["ws"] is not None:
-                ops.gemm_splitk(h, lw["fc2"], b["ws"], 2, res=x, out=x)
+            if ws is not None:
+                nxt = layers[i + 1]["n1"] if i + 1 < len(layers) else None  # the final norm has its own kernel
+                ops.gemm_splitk(h, lw["fc2"], ws, 2, res=x, out=x, norm_w=nxt, norm_out=xn if nxt is not None else None,
+                                norm_eps=self.eps)
+                normed = nxt is not None
             else:
                 ops.gemm(h, lw["fc2"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
         lens = b["lens"] if zero_padding else b["all_rows"]

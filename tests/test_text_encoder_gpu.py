@@ -68,6 +68,14 @@ def test_gemm_splitk(M, N, K, splits):
     x0 = x.clone()
     ops.gemm_splitk(a, w, ws, splits, res=x, out=x)            # in-place residual, no bias
     assert rel_l2(x, bf(x0.float() + bf(a.float() @ w.float().T).float())) < 4e-3
+    # the reduce launch can also apply the RMS norm that follows the projection
+    nw = bf(1 + 0.1 * torch.randn(N, generator=g)).to(DEV)
+    x = x0.clone()
+    xn = torch.empty_like(x)
+    ops.gemm_splitk(a, w, ws, splits, res=x, out=x, norm_w=nw, norm_out=xn)
+    assert rel_l2(x, bf(x0.float() + bf(a.float() @ w.float().T).float())) < 4e-3
+    ref_n = ops.rmsnorm(x, nw, 1e-6)
+    assert (xn == ref_n).float().mean().item() > 0.99 and rel_l2(xn, ref_n) < 2e-3
     with pytest.raises(RuntimeError, match="empty split"):
         ops.gemm_splitk(a[:, :128], w[:, :128], torch.empty(3 * M * N, dtype=torch.float32, device=DEV), 3)  # 2 k-blocks
 
