@@ -225,7 +225,7 @@ def text_encoder_sample(torch, dev):
     ms = st.elapsed_time(en) / 5
     del te, enc
     torch.cuda.empty_cache()
-    return {"ms_per_prompt": ms, "tokens": 200, "rows_computed": 256, "launches_per_prompt": 242,
+    return {"ms_per_prompt": ms, "tokens": 200, "rows_computed": 256, "launches_per_prompt": 195,
             "what": "WanTextEncoder.forward (synthetic tokenizer + umt5-xxl encoder, 24 blocks, dim 4096, bf16, random "
                     "init) for one 200-token prompt; the reference's op sequence in eager PyTorch on the same GPU: "
                     "20.8 ms (tools/t5_bench.py, profiles/r01_t5_bench.json)"}
