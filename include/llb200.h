@@ -146,6 +146,8 @@ int llb_peer_barrier(void* const* flags_peers_dev, int rank, int n_ranks, void* 
 #define LLB_EPI_BIAS_F32 5      /* y written as float32 (out is float*, ldo in floats): attention logits of the VAE decoder */
 #define LLB_EPI_BIAS_MUL 6      /* res * y: the gated FFN of the umT5 text encoder, fc1(x) * gelu(gate(x)) with
                                    res = gelu(gate(x)) from a BIAS_GELU_BF16 launch (wan/modules/t5.py:133) */
+#define LLB_EPI_GEGLU_BF16 8    /* gated FFN of the umT5 encoder in one launch: W = 256-row tiles of [128 gate rows | the 128 fc1
+                                   rows of the same outputs], out [M, N / 2] = bf16(fc1) * gelu_bf16(bf16(gate)) (t5.py:133) */
 #define LLB_EPI_BIAS_GELU_BF16 7 /* the umT5 GELU module (wan/modules/t5.py:46-50): the tanh formula evaluated op by
                                    op with a bf16 rounding after each, as the reference's tensor expression does */
 

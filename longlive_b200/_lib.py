@@ -18,7 +18,7 @@ LLB_MAX_SEGS = 4
 
 # epilogues (include/llb200.h)
 (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_SILU, EPI_BIAS_GATE_RES, EPI_BIAS_RES, EPI_BIAS_F32, EPI_BIAS_MUL,
- EPI_BIAS_GELU_BF16) = range(8)
+ EPI_BIAS_GELU_BF16, EPI_GEGLU_BF16) = range(9)
 
 
 class KvState(C.Structure):

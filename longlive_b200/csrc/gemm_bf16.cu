@@ -290,6 +290,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
+      if constexpr (BN == 256 && !kFp8) {
+        if (epi == LLB_EPI_GEGLU_BF16) {
+          // Gated FFN in one launch (umT5, wan/modules/t5.py:133): the weight rows of a 256-wide tile are 128 gate rows
+          // followed by the 128 fc1 rows of the same output columns, so this warp finds the gate slab (2c + h) and the
+          // fc1 slab 128 columns further in the same accumulator: out = bf16(fc1) * gelu_bf16_chain(bf16(gate)).
+          // thread == row writes 32 consecutive bf16 (64 bytes) per slab; the output has N / 2 columns.
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t vg[32], vf[32];
+            tmem_ld32(t_row + c * 64, vg);
+            tmem_ld32(t_row + (c + 2) * 64, vf);
+            tmem_wait_ld();
+            if (c == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_cluster(tempty_lead0 + 8u * acc);
+                else mbar_arrive(tempty_bar(acc));
+              }
+            }
+            const int grow = row_base + lane;
+            const int ocol = n_idx * 128 + (2 * c + h) * 32;
+            if (grow < p.M && ocol < p.N / 2) {
+              uint32_t o[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float g0 = gelu_bf16_chain_f(bf16_round(__uint_as_float(vg[2 * i])));
+                const float g1 = gelu_bf16_chain_f(bf16_round(__uint_as_float(vg[2 * i + 1])));
+                o[i] = pack_bf16x2(bf16_round(__uint_as_float(vf[2 * i])) * bf16_round(g0),
+                                   bf16_round(__uint_as_float(vf[2 * i + 1])) * bf16_round(g1));
+              }
+              uint4* orow = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(grow) * p.ldo + ocol);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) orow[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
+          }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int col0 = n_idx * BN + (2 * c + h) * 32;
@@ -485,7 +524,7 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
                 "gemm: leading dims must be 16-byte multiples");
   LLB_CHECK_ARG(!fp8 || (a_scale && w_scale && (reinterpret_cast<uintptr_t>(w_scale) & 15) == 0),
                 "gemm_fp8: needs a_scale[M] and a 16-byte aligned w_scale[N]");
-  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_BIAS_GELU_BF16, "gemm: unknown epilogue %d", epilogue);
+  LLB_CHECK_ARG(epilogue >= 0 && epilogue <= LLB_EPI_GEGLU_BF16, "gemm: unknown epilogue %d", epilogue);
   LLB_CHECK_ARG(epilogue != LLB_EPI_BIAS_F32 || ldo % 4 == 0, "gemm: fp32 output needs ldo %% 4 == 0");
   {
     const int nkb = (K + (fp8 ? 128 : kBK) - 1) / (fp8 ? 128 : kBK);
@@ -528,9 +567,17 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
       }
     }
   }
+  if (epilogue == LLB_EPI_GEGLU_BF16) {
+    // gate | fc1 interleaved in 256-row weight tiles: only 256-wide tiles see both halves of an output column
+    LLB_CHECK_ARG(!fp8 && N % 256 == 0 && bias == nullptr && k_splits == 1, "gemm: GEGLU needs N %% 256 == 0, no bias");
+    const int pair_waves = (((M + 2 * kBM - 1) / (2 * kBM)) * (N / 256) + sms / 2 - 1) / (sms / 2);
+    const int single_waves = (((M + kBM - 1) / kBM) * (N / 256) + sms - 1) / sms;
+    bn = 256;
+    pair = pair_waves * 420.0 <= single_waves * 446.0;
+  }
   // debugging / benchmarking override: LLB_GEMM_TILE="<pair 0|1>,<bn>"
   const char* force = getenv("LLB_GEMM_TILE");
-  if (force != nullptr && N > 64) {
+  if (force != nullptr && N > 64 && epilogue != LLB_EPI_GEGLU_BF16) {
     int fp = 0, fb = 0;
     if (sscanf(force, "%d,%d", &fp, &fb) == 2 && (fb == 128 || fb == 192 || fb == 256)) {
       pair = fp != 0;

@@ -13,14 +13,14 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_BF16, EPI_BIAS_MUL,
-                   EPI_BIAS_RES, EPI_BIAS_SILU, STEP_PARAMS_INT32, StepParams)
+                   EPI_BIAS_RES, EPI_BIAS_SILU, EPI_GEGLU_BF16, STEP_PARAMS_INT32, StepParams)
 
 __all__ = [
     "gemm", "gemm_splitk", "gemm_fp8", "quant_rows_fp8", "ln_modulate_fp8", "quantize_weight_e4m3", "attention", "ln_modulate", "rmsnorm", "rmsnorm_rope_append", "patchify", "unpatchify",
     "sinusoidal", "modulation_table", "silu", "make_step_params", "step_params_tensor",
     "build_rope_table", "launch_count",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_SILU", "EPI_BIAS_GATE_RES", "EPI_BIAS_RES", "EPI_BIAS_F32",
-    "EPI_BIAS_MUL", "EPI_BIAS_GELU_BF16", "embed_rows", "t5_attention", "t5_final_norm",
+    "EPI_BIAS_MUL", "EPI_BIAS_GELU_BF16", "EPI_GEGLU_BF16", "geglu_weight", "embed_rows", "t5_attention", "t5_final_norm",
 ]
 
 
@@ -58,7 +58,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     assert K == K2, (a.shape, w.shape)
     out_dtype = torch.float32 if epilogue == EPI_BIAS_F32 else torch.bfloat16
     if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        out = torch.empty((M, N // 2 if epilogue == EPI_GEGLU_BF16 else N), dtype=out_dtype, device=a.device)
     _req(out, "out", out_dtype)
     for t, n in ((bias, "bias"), (gate, "gate"), (res, "res")):
         if t is not None:
@@ -69,6 +69,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         rows_per_gate, gate_row0, _ptr(res), res.stride(0) if res is not None else 0, _stream())
     _lib.check(rc, "llb_gemm_bf16")
     return out
+
+
+def geglu_weight(gate_w: torch.Tensor, fc1_w: torch.Tensor) -> torch.Tensor:
+    """Weight layout of EPI_GEGLU_BF16: 256-row tiles of [128 gate rows | the 128 fc1 rows of the same output columns]."""
+    F, K = gate_w.shape
+    assert fc1_w.shape == (F, K) and F % 128 == 0
+    return torch.stack([gate_w.view(F // 128, 128, K), fc1_w.view(F // 128, 128, K)], dim=1).reshape(2 * F, K).contiguous()
 
 
 def gemm_splitk(a: torch.Tensor, w: torch.Tensor, workspace: torch.Tensor, k_splits: int,

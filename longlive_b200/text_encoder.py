@@ -8,15 +8,15 @@ Host-side mirror of the reference interface:
     HuggingfaceTokenizer      wan/modules/tokenizers.py:38-82
 
 The reference runs the encoder in bf16 (the pipeline is cast with `.to(dtype=torch.bfloat16)`, inference.py:134)
-as ~15 eager ops per block over all 512 padded positions.  Here one block is eight launches:
+as ~15 eager ops per block over all 512 padded positions.  Here one block is seven or eight launches:
 
     llb_rmsnorm                       norm1                                       (t5.py:57-62)
     llb_gemm_bf16  N = 3 * dim_attn   q | k | v fused, no bias                    (t5.py:92-94)
     llb_t5_attn                       bias + mask + softmax + PV per head, tcgen05 (t5.py:96-111)
     llb_gemm_bf16  + BIAS_RES         o projection, x + y (split-K for <= 256 rows) (t5.py:114, 166)
     llb_rmsnorm                       norm2
-    llb_gemm_bf16  + BIAS_GELU_BF16   gelu(gate(x)), the reference's bf16 op chain (t5.py:46-50, 125)
-    llb_gemm_bf16  + BIAS_MUL         fc1(x) * gelu(gate(x))                      (t5.py:133)
+    llb_gemm_bf16  + GEGLU_BF16       fc1(x) * gelu(gate(x)) in ONE launch: gate | fc1 rows interleaved per 256-wide
+                                      tile, gelu = the reference's bf16 op chain  (t5.py:46-50, 125, 133)
     llb_gemm_bf16  + BIAS_RES         fc2, x + y                                  (t5.py:135, 167)
 
 plus the embedding gather and the final norm fused with the zeroing of the padding rows: 194 launches for the
@@ -139,6 +139,9 @@ class UMT5Encoder(nn.Module):
                 "qkv": c(torch.cat([blk.attn.q.weight, blk.attn.k.weight, blk.attn.v.weight], 0)),
                 "o": c(blk.attn.o.weight), "gate": c(blk.ffn.gate[0].weight), "fc1": c(blk.ffn.fc1.weight),
                 "fc2": c(blk.ffn.fc2.weight), "pos": c(blk.pos_embedding.embedding.weight),
+                # gate | fc1 as ONE weight in the tile layout of EPI_GEGLU_BF16 (needs dim_ffn % 128 == 0)
+                "gf": ops.geglu_weight(c(blk.ffn.gate[0].weight), c(blk.ffn.fc1.weight))
+                if self.dim_ffn % 128 == 0 else None,
             })
         # offsets up to the padded row count occur (padding rows / masked keys), so the table covers those too
         P["lut"] = relative_position_buckets(self._rows_max(), self.num_buckets, self.max_dist).to(dev)
@@ -181,8 +184,13 @@ class UMT5Encoder(nn.Module):
             else:
                 ops.gemm(att, lw["o"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
                 ops.rmsnorm(x, lw["n2"], self.eps, out=xn)
-            ops.gemm(xn, lw["gate"], epilogue=ops.EPI_BIAS_GELU_BF16, out=g)
-            ops.gemm(xn, lw["fc1"], epilogue=ops.EPI_BIAS_MUL, res=g, out=h)
+            # one launch for gate and fc1, except at 129-256 rows where its 80 pair tiles of 256 x 256 spill into a
+            # second wave on 74 SM pairs while the two separate launches (54 tiles of 256 x 192 each) fit one wave each
+            if lw["gf"] is not None and not 128 < B * Lp <= 256:
+                ops.gemm(xn, lw["gf"], epilogue=ops.EPI_GEGLU_BF16, out=h)
+            else:
+                ops.gemm(xn, lw["gate"], epilogue=ops.EPI_BIAS_GELU_BF16, out=g)
+                ops.gemm(xn, lw["fc1"], epilogue=ops.EPI_BIAS_MUL, res=g, out=h)
             if ws is not None:
                 nxt = layers[i + 1]["n1"] if i + 1 < len(layers) else None  # the final norm has its own kernel
                 ops.gemm_splitk(h, lw["fc2"], ws, 2, res=x, out=x, norm_w=nxt, norm_out=xn if nxt is not None else None,

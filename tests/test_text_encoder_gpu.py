@@ -52,6 +52,23 @@ def test_gemm_mul_epilogue_and_no_bias():
         assert rel_l2(x, bf(x0.float() + bf(a.float() @ w.float().T).float())) < 4e-3
 
 
+@pytest.mark.parametrize("M,F,K", [(512, 10240, 4096), (256, 10240, 4096), (128, 640, 256), (200, 384, 264)])
+def test_gemm_geglu_epilogue(M, F, K):
+    """gate and fc1 of the gated FFN in one launch must equal the two-launch form (GELU_BF16 then MUL) bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    wg = bf(torch.randn(F, K, generator=g) * K ** -0.5).to(DEV)
+    wf = bf(torch.randn(F, K, generator=g) * K ** -0.5).to(DEV)
+    gate = ops.gemm(a, wg, epilogue=ops.EPI_BIAS_GELU_BF16)
+    two = ops.gemm(a, wf, epilogue=ops.EPI_BIAS_MUL, res=gate)
+    one = ops.gemm(a, ops.geglu_weight(wg, wf), epilogue=ops.EPI_GEGLU_BF16)
+    assert one.shape == (M, F)
+    assert torch.equal(one, two)
+    ref = bf(bf(a.float() @ wf.float().T).float() * torch.nn.functional.gelu(bf(a.float() @ wg.float().T).float(), approximate="tanh"))
+    assert rel_l2(one, ref) < 8e-3      # the bf16 op chain of the reference's GELU differs from the exact function
+
+
 @pytest.mark.parametrize("M,N,K,splits", [(256, 4096, 10240, 2), (128, 4096, 4096, 2), (200, 1032, 1000, 3), (256, 512, 192, 3)])
 def test_gemm_splitk(M, N, K, splits):
     ops = _ops()
