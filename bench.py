@@ -261,14 +261,16 @@ def full_pipeline_sample(torch, dev, pipe_args):
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
         pipe.inference(noise, [prompt])  # warm-up: graph captures
-        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        st.record()
-        video = pipe.inference(noise, [prompt], profile=True)
-        en.record()
-        torch.cuda.synchronize()
-    ms = st.elapsed_time(en)
-    prof = pipe.last_profile or {}
+        ms, prof = None, {}
+        for _ in range(2):  # best of two complete calls
+            st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            st.record()
+            video = pipe.inference(noise, [prompt], profile=True)
+            en.record()
+            torch.cuda.synchronize()
+            if ms is None or st.elapsed_time(en) < ms:
+                ms, prof = st.elapsed_time(en), pipe.last_profile or {}
     n_video = int(video.shape[1])
     return {"ms_total": ms, "video_frames": n_video, "video_fps_total": n_video / ms * 1e3,
             "ms_diffusion": prof.get("diffusion_ms"), "ms_vae": prof.get("vae_ms"), "ms_cache_init": prof.get("init_ms"),
