@@ -76,3 +76,18 @@ def test_non_prefix_mask_rejected():
     mask = torch.tensor([[1, 0, 1, 0, 0, 0, 0, 0]])
     with pytest.raises(ValueError, match="prefix"):
         enc(ids, mask)
+
+
+def test_geglu_weight_layout():
+    """EPI_GEGLU_BF16 expects 256-row tiles of [128 gate rows | the 128 fc1 rows of the same output columns]."""
+    from longlive_b200 import ops
+    F, K = 384, 16
+    gate = torch.arange(F * K, dtype=torch.float32).view(F, K)
+    fc1 = -gate
+    w = ops.geglu_weight(gate, fc1)
+    assert w.shape == (2 * F, K)
+    for t in range(F // 128):
+        assert torch.equal(w[t * 256:t * 256 + 128], gate[t * 128:(t + 1) * 128])
+        assert torch.equal(w[t * 256 + 128:(t + 1) * 256], fc1[t * 128:(t + 1) * 128])
+    with pytest.raises(AssertionError):
+        ops.geglu_weight(gate[:100], fc1[:100])
