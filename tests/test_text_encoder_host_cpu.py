@@ -91,3 +91,77 @@ def test_geglu_weight_layout():
         assert torch.equal(w[t * 256 + 128:(t + 1) * 256], fc1[t * 128:(t + 1) * 128])
     with pytest.raises(AssertionError):
         ops.geglu_weight(gate[:100], fc1[:100])
+
+
+class _RecordingOps:
+    """Stands in for longlive_b200.ops: records the launch sequence of UMT5Encoder._run without a GPU."""
+    EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU_BF16, EPI_BIAS_MUL, EPI_GEGLU_BF16 = 0, 4, 7, 6, 8
+
+    def __init__(self):
+        self.calls = []
+
+    def embed_rows(self, table, ids, rows, out=None):
+        self.calls.append(("embed",)); return out
+
+    def rmsnorm(self, x, w, eps, out=None):
+        self.calls.append(("norm", id(w))); return out
+
+    def gemm(self, a, w, bias=None, *, epilogue=0, out=None, res=None, **kw):
+        self.calls.append(("gemm", id(w), epilogue)); return out
+
+    def gemm_splitk(self, a, w, ws, k_splits, bias=None, *, res=None, out=None, norm_w=None, norm_out=None, norm_eps=0.0):
+        self.calls.append(("splitk", id(w), k_splits, id(norm_w) if norm_out is not None else None)); return out
+
+    def t5_attention(self, qkv, B, H, lens, pos, lut, out=None):
+        self.calls.append(("attn",)); return out
+
+    def t5_final_norm(self, x, w, B, rows_out, lens, eps, out=None):
+        self.calls.append(("final", id(w))); return out
+
+
+@pytest.mark.parametrize("rows,expect_split,expect_geglu", [(128, True, True), (256, True, False), (512, False, True)])
+def test_encoder_launch_sequence(monkeypatch, rows, expect_split, expect_geglu):
+    """Every block normalises exactly what the reference normalises (t5.py:163-168), whichever fusions are active:
+    short prompts use the split-K projections whose reduce launch applies the following norm, the gated FFN is one
+    launch except at 129-256 rows."""
+    import longlive_b200.text_encoder as te
+    rec = _RecordingOps()
+    monkeypatch.setattr(te, "ops", rec)
+    enc = UMT5Encoder(vocab=50, dim=128, dim_attn=128, dim_ffn=256, num_heads=2, num_layers=3, text_len=512)
+    z = lambda *s: torch.zeros(*s)
+    layers = [{k: z(1) for k in ("n1", "n2", "qkv", "o", "gate", "fc1", "fc2", "pos", "gf")} for _ in range(3)]
+    enc._packed = {"emb": z(1), "norm": z(1), "lut": z(1), "layers": layers}
+    b = {k: z(1) for k in ("x", "xn", "qkv", "att", "g", "h", "out", "ids", "lens")}
+    b["ws"] = z(1) if rows <= 256 else None
+    enc._run(b, 1, rows, 512, True)
+    names = [c[0] for c in rec.calls]
+    assert names[0] == "embed" and names[-1] == "final" and names.count("attn") == 3
+    # norm1 of block 0 is always its own launch; later norm1s and every norm2 are either a launch or fused into a reduce
+    norm_launch = [c[1] for c in rec.calls if c[0] == "norm"]
+    fused = [c[3] for c in rec.calls if c[0] == "splitk" and c[3] is not None]
+    want = []
+    for lw in layers:
+        want += [id(lw["n1"]), id(lw["n2"])]
+    assert sorted(norm_launch + fused) == sorted(want)
+    assert norm_launch[0] == id(layers[0]["n1"])
+    # order inside a block: (norm1) qkv attn o (norm2) ffn fc2
+    i = 0
+    for li, lw in enumerate(layers):
+        if li == 0 or not expect_split:
+            assert rec.calls[i + 1] == ("norm", id(lw["n1"])); i += 1
+        assert rec.calls[i + 1][:2] == ("gemm", id(lw["qkv"])); assert rec.calls[i + 2] == ("attn",); i += 2
+        if expect_split:
+            assert rec.calls[i + 1] == ("splitk", id(lw["o"]), 2, id(lw["n2"])); i += 1
+        else:
+            assert rec.calls[i + 1] == ("gemm", id(lw["o"]), rec.EPI_BIAS_RES); assert rec.calls[i + 2] == ("norm", id(lw["n2"])); i += 2
+        if expect_geglu:
+            assert rec.calls[i + 1] == ("gemm", id(lw["gf"]), rec.EPI_GEGLU_BF16); i += 1
+        else:
+            assert rec.calls[i + 1] == ("gemm", id(lw["gate"]), rec.EPI_BIAS_GELU_BF16)
+            assert rec.calls[i + 2] == ("gemm", id(lw["fc1"]), rec.EPI_BIAS_MUL); i += 2
+        if expect_split:
+            nxt = id(layers[li + 1]["n1"]) if li + 1 < 3 else None
+            assert rec.calls[i + 1] == ("splitk", id(lw["fc2"]), 2, nxt); i += 1
+        else:
+            assert rec.calls[i + 1] == ("gemm", id(lw["fc2"]), rec.EPI_BIAS_RES); i += 1
+    assert rec.calls[i + 1] == ("final", id(enc._packed["norm"]))
