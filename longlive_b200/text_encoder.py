@@ -19,8 +19,10 @@ as ~15 eager ops per block over all 512 padded positions.  Here one block is sev
                                       tile, gelu = the reference's bf16 op chain  (t5.py:46-50, 125, 133)
     llb_gemm_bf16  + BIAS_RES         fc2, x + y                                  (t5.py:135, 167)
 
-plus the embedding gather and the final norm fused with the zeroing of the padding rows: 194 launches for the
-24-block encoder, replayed as one CUDA graph per (batch, rows) shape.  Keys at or beyond a prompt's length have
+(at <= 256 rows o and fc2 are split-K launches whose reduce launch also applies the norm that follows, so norm2 and the
+next block's norm1 are not launches of their own; at 129-256 rows the gated FFN is two launches) plus the embedding gather
+and the final norm fused with the zeroing of the padding rows: 170-195 launches for the 24-block encoder, replayed as one
+CUDA graph per (batch, rows) shape.  Keys at or beyond a prompt's length have
 probability exactly 0 (the reference fills them with finfo.min before an fp32 softmax), so padded rows never
 influence valid rows, and WanTextEncoder zeroes them at the end: with `trim_padding` (default) only the first
 round_up(max valid length, 128) rows are computed at all.
