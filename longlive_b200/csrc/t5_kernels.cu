@@ -100,9 +100,9 @@ t5_final_norm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bflo
 //   logits = bf16(logits + bias[h][key - query])    bias = per-block bucket table, buckets from a host LUT
 //   masked keys (key >= seq_len)  ->  probability exactly 0  (reference: finfo.min before the fp32 softmax)
 //   out = bf16(bf16(softmax_fp32(logits)) V)
-// (A register-level mma.sync.m16n8k16 version of this kernel was written first and ran at the same speed -
-// 32 us per launch at 512 rows, both are bound by the per-element softmax work of 128-256 threads per SM;
-// the tensor-core version below replaced it.)
+// (A register-level mma.sync.m16n8k16 version of this kernel was written first: 32 us per launch at 512 rows; the
+// tcgen05 version below started at the same time - both bound by the per-element softmax work of 128-512 threads
+// per SM -, reached 23 us with the packed bias / rounding pass and replaced it.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kT5D = 64;
 
