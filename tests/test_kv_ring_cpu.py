@@ -104,3 +104,77 @@ def test_planner_rejects_bad_arguments():
         ring.plan(0, 0)
     with pytest.raises(RuntimeError):
         ring.plan(-5, 10)
+
+
+def _pipeline_calls(rng, T, chunk, local, switches):
+    """The call pattern of the two pipelines (causal_inference.py:139-200, interactive...:283-330): per chunk four
+    denoising calls + one clean-context call at the same position; at a prompt switch one recache call over the
+    last min(local, start) frames first."""
+    calls, start = [], 0
+    while start < T:
+        if start in switches and start > 0:
+            n = start if local == -1 else min(local, start)
+            calls.append(("recache", start - n, n))
+        for _ in range(5):
+            calls.append(("denoise", start, chunk))
+        start += chunk
+    return calls
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_planner_matches_oracle_on_random_pipelines(seed):
+    """Beyond the 12 recorded reference traces: random geometry (tokens per frame, sink, window, chunk, video
+    length, switch points, both global_sink settings) driven with the pipelines' call pattern; the C planner must
+    agree with the pure-Python restatement of the reference on every integer, on the attended key SET and on the
+    logical cache content."""
+    import random
+    rng = random.Random(seed)
+    fs = rng.choice([1, 3, 4, 7])
+    chunk = rng.choice([1, 2, 3])
+    sink = rng.choice([0, 1, 2, 3])
+    T = chunk * rng.randint(4, 24)
+    if rng.random() < 0.2:
+        local, size_frames = -1, T  # global attention: the cache holds the whole video, never rolls
+    else:
+        local = max(sink + chunk, rng.randint(sink + chunk, sink + 4 * chunk + 3))
+        size_frames = local
+    global_sink = rng.random() < 0.5
+    size, S = size_frames * fs, sink * fs
+    M = 32760 if local == -1 else local * fs
+    switches = set(rng.sample(range(chunk, T, chunk), k=min(3, len(range(chunk, T, chunk))))) if rng.random() < 0.7 else set()
+    ring = KvRing(size, S, M, local)
+    sim = RefCacheSim(size, S, M, local)
+    phys = [None] * size
+    for ci, (kind, f0, nf) in enumerate(_pipeline_calls(rng, T, chunk, local, switches)):
+        cur, n = f0 * fs, nf * fs
+        recache = kind == "recache"
+        sink_recache = recache and not global_sink
+        if sink_recache:
+            sim.zero()
+            phys = [None] * size
+        labels = [(ci, i) for i in range(n)]
+        o = sim.step(cur, n, labels, sink_recache)
+        p = ring.plan(cur, n, sink_recache)
+        ctx = f"seed {seed} call {ci} {kind} fs={fs} chunk={chunk} sink={sink} local={local} gs={global_sink}"
+        assert p.action == o["action"] and p.is_recompute == o["is_recompute"], ctx
+        assert p.current_end == o["current_end"], ctx
+        assert (p.local_start, p.local_end) == (o["local_start_index"], o["local_end_index"]), ctx
+        assert (p.write_start, p.write_end, p.write_len) == (o["write_start_index"], o["write_end_index"], o["write_len"]), ctx
+        assert p.roped_offset == o["roped_offset"], ctx
+        if o["action"] == "roll_and_insert":
+            assert (p.num_evicted, p.num_rolled) == (o["num_evicted"], o["num_rolled"]), ctx
+        assert sum(nw for _, _, nw in p.writes) == p.write_len, ctx
+        for (src, dst, nw) in p.writes:
+            assert 0 <= dst and dst + nw <= size, ctx
+            phys[dst:dst + nw] = labels[src:src + nw]
+        attended = []
+        for (s, ln) in p.attn_segs:
+            assert 0 <= s and s + ln <= size and ln > 0, ctx
+            attended += phys[s:s + ln]
+        key = lambda x: (-1, -1) if x is None else x
+        assert sorted(attended, key=key) == sorted(o["attended"], key=key), ctx
+        ring.commit(p)
+        assert (ring.global_end, ring.local_end) == (o["global_end_after"], o["local_end_after"]), ctx
+        idx = ring.logical_index().tolist()
+        for pos in range(ring.local_end):
+            assert phys[idx[pos]] == sim.slots[pos], ctx
