@@ -178,3 +178,57 @@ def test_planner_matches_oracle_on_random_pipelines(seed):
         idx = ring.logical_index().tolist()
         for pos in range(ring.local_end):
             assert phys[idx[pos]] == sim.slots[pos], ctx
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/wan/modules"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_live_reference_on_random_geometry(seed):
+    """Pins oracle/kv_index.py beyond the recorded traces: a tiny REAL reference model (its own cache logic, spied at
+    _apply_cache_updates) is driven with the pipelines' call pattern on random geometry; every integer must match."""
+    import random
+    import torch
+    from oracle import make_golden as mg
+    from oracle import ref_shims
+    from oracle import wan_oracle as wo
+    rng = random.Random(100 + seed)
+    H, W = rng.choice([(2, 2), (2, 6), (4, 4), (4, 6)])
+    fs = (H // 2) * (W // 2)
+    chunk = rng.choice([1, 2, 3])
+    sink = rng.choice([0, 1, 2, 3])
+    T = chunk * rng.randint(4, 10)
+    local = -1 if seed == 5 else rng.randint(sink + chunk, sink + 3 * chunk + 2)
+    global_sink = rng.random() < 0.5
+    switches = sorted(rng.sample(range(chunk, T, chunk), k=min(2, len(range(chunk, T, chunk)))))
+    cfg = wo.WanConfig(dim=16, ffn_dim=16, num_heads=2, num_layers=1, text_dim=8, text_len=4,
+                       local_attn_size=local, sink_size=sink, frame_seqlen=fs)
+    model = ref_shims.build_reference_model(cfg, wo.init_state_dict(cfg, seed=0), "sdpa")
+    log = []
+    mg.spy_model(model, log)
+    size = (local if local != -1 else T) * fs
+    kv = wo.new_kv_cache(cfg, 1, size, "cpu")
+    cc = wo.new_crossattn_cache(cfg, 1, "cpu")
+    ctx = wo.synth_prompt_embeds(cfg, 1, 3)
+    S, M = sink * fs, (32760 if local == -1 else local * fs)
+    sim = RefCacheSim(size, S, M, local)
+    for ci, (start, n, kind, seg) in enumerate(mg.call_pattern(T, chunk, switches, local)):
+        recache = kind == "recache"
+        if recache:
+            if not global_sink:
+                for c in kv:
+                    c["k"].zero_(); c["v"].zero_()
+                sim.zero()
+            for c in cc:
+                c["is_init"] = False
+        x = torch.zeros(1, 16, n, H, W, dtype=torch.bfloat16)
+        with torch.no_grad():
+            model(x, t=torch.zeros(1, n), context=ctx, seq_len=1 << 20, kv_cache=kv, crossattn_cache=cc,
+                  current_start=start * fs, sink_recache_after_switch=(recache and not global_sink))
+        g = log[-1]
+        o = sim.step(start * fs, n * fs, [(ci, i) for i in range(n * fs)], recache and not global_sink)
+        ctxs = f"seed {seed} call {ci} {kind}: fs={fs} chunk={chunk} sink={sink} local={local} gs={global_sink}"
+        for k in ("action", "is_recompute", "current_end", "local_start_index", "local_end_index",
+                  "write_start_index", "write_end_index", "global_end_after", "local_end_after"):
+            assert o[k] == g[k], f"{ctxs}: {k} oracle {o[k]} != reference {g[k]}"
+        assert o["new_tokens"] == g["new_tokens"], ctxs
+        if g["action"] == "roll_and_insert":
+            assert (o["num_evicted"], o["num_rolled"]) == (g["num_evicted"], g["num_rolled"]), ctxs
