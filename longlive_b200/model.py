@@ -293,6 +293,58 @@ class CausalWanModel(nn.Module):
             cc["is_init"] = True
 
     # ------------------------------------------------------------------------------------------
+    def _run_block(self, i: int, b: dict, kv_cache, crossattn_cache, B: int, F: int, H: int, W: int):
+        """Block i (reference CausalWanAttentionBlock.forward, causal_model.py:413-477) as 13 launches,
+        in place on the residual stream b["x"]; reads its adaLN rows from b["mod"][i]."""
+        P = self._packed
+        C_, nh, eps = self.dim, self.num_heads, self.eps
+        gh, gw = H // 2, W // 2
+        fs = gh * gw
+        L = F * fs
+        v = self.attn_variant
+        x, xm = b["x"], b["xm"]
+        f8 = self.fp8_linears
+        lw = P["layers"][i]
+
+        def lin(name, a, **kw):
+            """One block Linear: bf16 tcgen05 GEMM, or W8A8 (a = (a8, scale)) when fp8_linears."""
+            if f8:
+                return ops.gemm_fp8(a[0], a[1], lw[name + "_w8"], lw[name + "_ws"], lw[name + "_b"], **kw)
+            return ops.gemm(a, lw[name + "_w"], lw[name + "_b"], **kw)
+
+        def ln_in(**kw):
+            """LayerNorm(+modulate) producing the next Linear's input (bf16, or e4m3 + row scales)."""
+            if f8:
+                return ops.ln_modulate_fp8(x, b["a8"], b["sa"], eps=eps, **kw)
+            return ops.ln_modulate(x, eps=eps, out=xm, **kw)
+
+        def act_in(t, buf="a8"):
+            return ops.quant_rows_fp8(t, b[buf], b["sa"]) if f8 else t
+
+        m = b["mod"][i]  # [B*F, 6C]
+        e = [m[:, k * C_:(k + 1) * C_] for k in range(6)]
+        lin("qkv", ln_in(shift=e[0], scale=e[1], rows_per_frame=fs), out=b["qkv"])
+        kc, vc = kv_cache[i]["k"], kv_cache[i]["v"]
+        for bi in range(B):
+            rows = slice(bi * L, (bi + 1) * L)
+            k2, v2 = kc[bi].view(-1, C_), vc[bi].view(-1, C_)
+            ops.rmsnorm_rope_append(b["qkv"][rows], b["q"][rows], k2, v2, lw["nq"], lw["nk"], P["rope"],
+                                    (gh, gw), b["params"], n_heads=nh, eps=eps)
+            ops.attention(b["q"][rows], k2, v2, b["params"], n_heads=nh, out=b["attn"][rows], variant=v)
+        lin("o", act_in(b["attn"]), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2], rows_per_gate=fs,
+            res=x, out=x)
+        lin("cq", ln_in(ln_w=lw["n3_w"], ln_b=lw["n3_b"]), out=b["cq"])
+        ops.rmsnorm(b["cq"], lw["cnq"], eps, out=b["q"])
+        ck, cv = crossattn_cache[i]["k"], crossattn_cache[i]["v"]
+        for bi in range(B):
+            rows = slice(bi * L, (bi + 1) * L)
+            ops.attention(b["q"][rows], ck[bi].view(-1, C_), cv[bi].view(-1, C_), P["cross_segs"],
+                          n_heads=nh, out=b["attn"][rows], variant=v)
+        lin("co", act_in(b["attn"]), epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+        lin("f1", ln_in(shift=e[3], scale=e[4], rows_per_frame=fs), epilogue=ops.EPI_BIAS_GELU, out=b["h"])
+        lin("f2", act_in(b["h"], "h8"), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
+            res=x, out=x)
+
     def _run_blocks(self, b: dict, kv_cache, crossattn_cache, B: int, F: int, H: int, W: int):
         """The captured part: everything between the static input buffers and the static output."""
         P = self._packed
@@ -311,48 +363,9 @@ class CausalWanModel(nn.Module):
         ops.silu(b["e"], out=b["es"])
         ops.gemm(b["es"], P["tproj_w"], P["tproj_b"], out=b["e0"])
         ops.modulation_table(P["mod_all"], b["e0"], out=b["mod"])
+        for i in range(len(P["layers"])):
+            self._run_block(i, b, kv_cache, crossattn_cache, B, F, H, W)
         x, xm = b["x"], b["xm"]
-        f8 = self.fp8_linears
-
-        def lin(name, lw, a, **kw):
-            """One block Linear: bf16 tcgen05 GEMM, or W8A8 (a = (a8, scale)) when fp8_linears."""
-            if f8:
-                return ops.gemm_fp8(a[0], a[1], lw[name + "_w8"], lw[name + "_ws"], lw[name + "_b"], **kw)
-            return ops.gemm(a, lw[name + "_w"], lw[name + "_b"], **kw)
-
-        def ln_in(**kw):
-            """LayerNorm(+modulate) producing the next Linear's input (bf16, or e4m3 + row scales)."""
-            if f8:
-                return ops.ln_modulate_fp8(x, b["a8"], b["sa"], eps=eps, **kw)
-            return ops.ln_modulate(x, eps=eps, out=xm, **kw)
-
-        def act_in(t, buf="a8"):
-            return ops.quant_rows_fp8(t, b[buf], b["sa"]) if f8 else t
-
-        for i, lw in enumerate(P["layers"]):
-            m = b["mod"][i]  # [B*F, 6C]
-            e = [m[:, k * C_:(k + 1) * C_] for k in range(6)]
-            lin("qkv", lw, ln_in(shift=e[0], scale=e[1], rows_per_frame=fs), out=b["qkv"])
-            kc, vc = kv_cache[i]["k"], kv_cache[i]["v"]
-            for bi in range(B):
-                rows = slice(bi * L, (bi + 1) * L)
-                k2, v2 = kc[bi].view(-1, C_), vc[bi].view(-1, C_)
-                ops.rmsnorm_rope_append(b["qkv"][rows], b["q"][rows], k2, v2, lw["nq"], lw["nk"], P["rope"],
-                                        (gh, gw), b["params"], n_heads=nh, eps=eps)
-                ops.attention(b["q"][rows], k2, v2, b["params"], n_heads=nh, out=b["attn"][rows], variant=v)
-            lin("o", lw, act_in(b["attn"]), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2], rows_per_gate=fs,
-                res=x, out=x)
-            lin("cq", lw, ln_in(ln_w=lw["n3_w"], ln_b=lw["n3_b"]), out=b["cq"])
-            ops.rmsnorm(b["cq"], lw["cnq"], eps, out=b["q"])
-            ck, cv = crossattn_cache[i]["k"], crossattn_cache[i]["v"]
-            for bi in range(B):
-                rows = slice(bi * L, (bi + 1) * L)
-                ops.attention(b["q"][rows], ck[bi].view(-1, C_), cv[bi].view(-1, C_), P["cross_segs"],
-                              n_heads=nh, out=b["attn"][rows], variant=v)
-            lin("co", lw, act_in(b["attn"]), epilogue=ops.EPI_BIAS_RES, res=x, out=x)
-            lin("f1", lw, ln_in(shift=e[3], scale=e[4], rows_per_frame=fs), epilogue=ops.EPI_BIAS_GELU, out=b["h"])
-            lin("f2", lw, act_in(b["h"], "h8"), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
-                res=x, out=x)
         # head (causal_model.py:497-508): modulation [1,2,C] + e [B,F,1,C]
         b["e2"][:, :C_].copy_(b["e"]); b["e2"][:, C_:].copy_(b["e"])
         ops.modulation_table(P["head_mod"], b["e2"], out=b["hmod"])
@@ -429,6 +442,36 @@ class CausalWanModel(nn.Module):
         ring.commit(plan)
         self._publish_indices(kv_cache, ring)
         return b["out"].to(x.dtype).clone()
+
+    @torch.no_grad()
+    def forward_block(self, i: int, x_tokens: torch.Tensor, e0: torch.Tensor, kv_cache, crossattn_cache,
+                      current_start: int, grid, sink_recache_after_switch: bool = False,
+                      commit: bool = False) -> torch.Tensor:
+        """Block i alone (reference CausalWanAttentionBlock.forward, causal_model.py:413-477) on a
+        caller-supplied residual stream: x_tokens [B, L, C], e0 [B, F, 6, C] (time_projection output,
+        :979), grid = (F, h, w) in patches.  Cross-attention caches must already be initialised.
+        The ring is planned like in forward(); it is committed only when `commit` (one block is not
+        a whole forward).  Used for teacher-forced per-block parity (tests/test_block_teacher_gpu.py)."""
+        if self._packed is None:
+            self._pack()
+        B, L, C_ = x_tokens.shape
+        F, gh, gw = grid
+        assert L == F * gh * gw and C_ == self.dim and all(cc["is_init"] for cc in crossattn_cache)
+        b = self._workspace_for(B, F, 2 * gh, 2 * gw, x_tokens.device)
+        ring = self._ring_of(kv_cache, gh * gw)
+        plan = ring.plan(current_start, L, sink_recache_after_switch)
+        self._upload_params(ring.step_params(plan, current_start // (gh * gw)), b["params"])
+        self.last_plan = plan
+        b["x"].copy_(x_tokens.reshape(B * L, C_).to(torch.bfloat16))
+        b["e0"].copy_(e0.reshape(B * F, 6 * C_).to(torch.bfloat16))
+        n0 = ops.launch_count()
+        ops.modulation_table(self._packed["mod_all"], b["e0"], out=b["mod"])
+        self._run_block(i, b, kv_cache, crossattn_cache, B, F, 2 * gh, 2 * gw)
+        self.kernel_launches += ops.launch_count() - n0
+        if commit:
+            ring.commit(plan)
+            self._publish_indices(kv_cache, ring)
+        return b["x"].view(B, L, C_).clone()
 
     def _publish_indices(self, kv_cache, ring: KvRing):
         """Keep kv_cache[*]['global_end_index'/'local_end_index'] observable with reference values.

@@ -66,3 +66,18 @@ def run_pipeline(gen: OracleGenerator, cfg: WanConfig, noise: torch.Tensor, prom
         start += F
         block += 1
     return out, kv
+
+
+class DeviceSeededNoise:
+    """Deterministic stand-in for torch.randn_like in the pipelines' re-noising step, drawn ON the
+    device (call k uses seed 7000 + k), so that long runs are not throttled by host RNG + H2D copies.
+    The oracle pipeline and the CUDA pipeline consume identical draws when both run on the same GPU."""
+
+    def __init__(self, device):
+        self.k = 0
+        self.g = torch.Generator(device=device)
+
+    def __call__(self, like, *a, **kw):
+        self.g.manual_seed(7000 + self.k)
+        self.k += 1
+        return torch.randn(like.shape, generator=self.g, device=like.device, dtype=torch.float32).to(like.dtype)
