@@ -16,11 +16,41 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("LLB_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the unmodified reference tree as shipped to the GPU box: __graft_entry__.build() mirrors
+# /root/reference (minus assets) into baseline/_ref/ (git-ignored, travels with gpurun)
+SHIPPED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _has_tree(root: str) -> bool:
+    return os.path.isdir(os.path.join(root, "wan", "modules"))
+
+
+def _default_root() -> str:
+    env = os.environ.get("LLB_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if _has_tree("/root/reference") else SHIPPED_ROOT
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "wan", "modules"))
+    return _has_tree(REFERENCE_ROOT)
+
+
+def shipped_available() -> bool:
+    return _has_tree(SHIPPED_ROOT)
+
+
+def use_shipped_copy() -> None:
+    """GPU tests / bench.py: import the reference from baseline/_ref only (never /root/reference)."""
+    global REFERENCE_ROOT
+    if not shipped_available():
+        raise RuntimeError(f"no shipped reference tree at {SHIPPED_ROOT}: run __graft_entry__.build() in the "
+                           "build container first")
+    REFERENCE_ROOT = SHIPPED_ROOT
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -35,7 +65,8 @@ def install(attention_impl: str = "sdpa"):
 
     attention_impl: 'sdpa' -> torch SDPA stands in for flash-attn (same maths: scale 1/sqrt(d), no
     mask); 'exact' -> oracle.wan_oracle.exact_attention (used to show that everything *around*
-    attention is bit-identical between the oracle and the reference).
+    attention is bit-identical between the oracle and the reference); 'flash' -> nothing is patched:
+    the reference's own flash-attn call (wan/modules/attention.py:131-145), CUDA only.
     """
     if not available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
@@ -82,6 +113,22 @@ def install(attention_impl: str = "sdpa"):
     mm = importlib.import_module("wan.modules.model")
 
     # (4) attention entry points
+    if attention_impl == "flash":
+        if not torch.cuda.is_available():
+            raise RuntimeError("attention_impl='flash' runs the reference's flash-attn path: CUDA only")
+        am = importlib.import_module("wan.modules.attention")
+        cm.attention = am.attention                  # undo an earlier patch in this process
+        mm.flash_attention = am.flash_attention
+        return cm, mm
+    if attention_impl == "fallback":
+        # the reference's OWN no-flash-attn branch (wan/modules/attention.py:183-197: torch SDPA), selected by
+        # clearing its availability flags; the direct flash_attention() call of the cross-attention
+        # (wan/modules/model.py:189) asserts CUDA, so on a CPU box it is routed through the same branch
+        am = importlib.import_module("wan.modules.attention")
+        am.FLASH_ATTN_2_AVAILABLE = am.FLASH_ATTN_3_AVAILABLE = False
+        cm.attention = am.attention
+        mm.flash_attention = lambda q, k, v, *a, **kw: am.attention(q, k, v)
+        return cm, mm
     if attention_impl == "exact":
         from oracle.wan_oracle import exact_attention
 
@@ -97,14 +144,28 @@ def install(attention_impl: str = "sdpa"):
     return cm, mm
 
 
-def build_reference_model(cfg, state_dict, attention_impl: str = "sdpa"):
-    """Instantiates the reference CausalWanModel with the oracle's config + weights (bf16, eval)."""
+def build_reference_model(cfg, state_dict, attention_impl: str = "sdpa", device=None):
+    """Instantiates the reference CausalWanModel with the oracle's config + weights (bf16, eval).
+    device: construct (and run init_weights) directly on that device - seconds instead of a minute
+    for the 1.4 B-parameter shape."""
+    import contextlib
     cm, _ = install(attention_impl)
-    model = cm.CausalWanModel(
+    with (torch.device(device) if device is not None else contextlib.nullcontext()):
+        model = _construct(cm, cfg)
+    if device is not None:
+        state_dict = {k: v.to(device) for k, v in state_dict.items()}
+    return _finish(model, cfg, state_dict)
+
+
+def _construct(cm, cfg):
+    return cm.CausalWanModel(
         model_type="t2v", patch_size=cfg.patch, text_len=cfg.text_len, in_dim=cfg.in_dim, dim=cfg.dim,
         ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim, text_dim=cfg.text_dim, out_dim=cfg.out_dim,
         num_heads=cfg.num_heads, num_layers=cfg.num_layers, local_attn_size=cfg.local_attn_size,
         sink_size=cfg.sink_size, qk_norm=True, cross_attn_norm=True, eps=cfg.eps)
+
+
+def _finish(model, cfg, state_dict):
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not unexpected, unexpected
     assert all("freqs" in m for m in missing), missing
@@ -117,10 +178,10 @@ def build_reference_model(cfg, state_dict, attention_impl: str = "sdpa"):
     return model
 
 
-def build_reference_wrapper(cfg, state_dict, shift: float = 5.0, attention_impl: str = "sdpa"):
+def build_reference_wrapper(cfg, state_dict, shift: float = 5.0, attention_impl: str = "sdpa", device=None):
     """The reference's WanDiffusionWrapper around a directly-constructed model (its __init__ needs
     checkpoint files, utils/wan_wrapper.py:132-133)."""
-    model = build_reference_model(cfg, state_dict, attention_impl)
+    model = build_reference_model(cfg, state_dict, attention_impl, device)
     cur = torch.cuda.current_device
     if not torch.cuda.is_available():
         torch.cuda.current_device = lambda: 0  # wan/modules/t5.py evaluates it at class-definition time
