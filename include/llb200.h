@@ -220,8 +220,11 @@ int llb_ln_modulate(const void* x, int64_t ldx, void* out, int64_t ldo, int rows
  * and the KV-cache insert (:268-269 / :310-311) in one pass over the fused QKV GEMM output.
  *   qkv [rows, ld_qkv] = q | k | v column blocks of width C = n_heads*128.
  *   q_out [rows, ldq] roped queries; k/v written to the ring rows given by p_dev->write_*.
- *   rope_cs: float2 [1024][64] (cos, sin) table; token -> (frame, h, w) row-major over
- *   (frames, grid_h, grid_w).  k_cache/v_cache may be null (norm + rope only). */
+ *   rope_cs: float2 [LLB_ROPE_MAX_POS][64] (cos, sin) table; token -> (frame, h, w) row-major over
+ *   (frames, grid_h, grid_w).  k_cache/v_cache may be null (norm + rope only).
+ *   The caller guarantees p_dev->rope_start_frame + frames <= LLB_ROPE_MAX_POS (the reference fails
+ *   there too: freqs[0][start:start+f] comes back short, causal_model.py:46-52). */
+#define LLB_ROPE_MAX_POS 1024
 int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_out, int64_t ldq,
                             void* k_cache, void* v_cache, int64_t ld_cache, int rows, int n_heads,
                             const void* wq, const void* wk, float eps, const void* rope_cs,

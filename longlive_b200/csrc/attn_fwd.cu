@@ -1382,12 +1382,7 @@ template <bool kPTmem, int kPoly, bool kHalf = false, bool kWide = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
   using Cfg = AttnCfg<kPTmem, kWide>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  LLB_SET_MAX_SMEM((attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>), Cfg::kSmemBytes);
   // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
   // partial-merge flag wait relies on
   cudaLaunchConfig_t cfg = {};

@@ -414,12 +414,7 @@ conv3d_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant
 template <int BN, int CK, int CPS, bool kNorm, int MT>
 static int launch_conv_n(const CUtensorMap& ti, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN, CK, CPS, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(conv3d_kernel<BN, CK, CPS, kNorm, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  LLB_SET_MAX_SMEM((conv3d_kernel<BN, CK, CPS, kNorm, MT>), Cfg::kSmemBytes);
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.T * p.tiles_h * p.tiles_w * p.num_n_tiles;

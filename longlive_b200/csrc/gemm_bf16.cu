@@ -477,12 +477,7 @@ template <int BN, bool kFp8, bool kPair>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN, kPair>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LLB_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kFp8, kPair>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  LLB_SET_MAX_SMEM((gemm_bf16_kernel<BN, kFp8, kPair>), Cfg::kSmemBytes);
   const int sms = device_sm_count();
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;

@@ -138,11 +138,14 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];  // zero-initialised; keyed by device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }

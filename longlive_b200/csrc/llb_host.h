@@ -61,7 +61,23 @@ int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint6
 int make_tmap_2d_bf16_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t ld, uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
+// SM count of the CURRENT device (cached per device ordinal).
 int device_sm_count();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per (kernel
+// instantiation, device ordinal), thread-safe.  Pass the kernel in parentheses if its template
+// argument list contains commas.
+#define LLB_SET_MAX_SMEM(kernel, bytes)                                                             \
+  do {                                                                                              \
+    static std::atomic<uint64_t> done_{0};                                                          \
+    int dev_ = 0;                                                                                   \
+    LLB_CUDA(cudaGetDevice(&dev_));                                                                 \
+    const uint64_t bit_ = 1ull << (dev_ & 63);                                                      \
+    if (!(done_.load(std::memory_order_acquire) & bit_)) {                                          \
+      LLB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));   \
+      done_.fetch_or(bit_, std::memory_order_release);                                              \
+    }                                                                                               \
+  } while (0)
 
 // Programmatic dependent launch is opt-in: LLB_PDL=1 (read once).
 bool pdl_enabled();

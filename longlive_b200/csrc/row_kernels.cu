@@ -609,6 +609,12 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
   LLB_CHECK_ARG((k_cache == nullptr) == (v_cache == nullptr), "rmsnorm_rope_append: k/v cache mismatch");
   LLB_CHECK_ARG(ld_qkv % 8 == 0 && ldq % 8 == 0 && ld_cache % 8 == 0 && grid_h > 0 && grid_w > 0,
                 "rmsnorm_rope_append: bad strides / grid");
+  // the (cos, sin) table has LLB_ROPE_MAX_POS rows per axis (the reference's freqs[1024], causal_model.py:622-629);
+  // the frame offset lives in device memory (p_dev->rope_start_frame), so the caller bounds start_frame + frames
+  LLB_CHECK_ARG(grid_h <= LLB_ROPE_MAX_POS && grid_w <= LLB_ROPE_MAX_POS &&
+                    (rows + grid_h * grid_w - 1) / (grid_h * grid_w) <= LLB_ROPE_MAX_POS,
+                "rmsnorm_rope_append: grid %d x %d / %d rows exceed the %d-position RoPE table", grid_h, grid_w, rows,
+                LLB_ROPE_MAX_POS);
   const int grid = (rows + kRowWarps - 1) / kRowWarps;
   auto kern = (C + 255) / 256 <= 6 ? rmsnorm_rope_append_kernel<6> : rmsnorm_rope_append_kernel<kMaxVec>;
   // grid.y: q / k / v parts; without a cache (norm + rope only) and unsharded there is nothing to do for v

@@ -423,10 +423,12 @@ extern "C" int llb_t5_attn(const void* qkv, int64_t ld_qkv, void* out, int64_t l
     int cap = max_seq_len > 0 && max_seq_len < rows_per_seq ? max_seq_len : rows_per_seq;
     cap = (cap + 127) & ~127;
     const size_t smem_tc = 1024 + 1024 + 16384 + static_cast<size_t>(cap) * 256 + (2 * rows_per_seq - 1) * sizeof(float);
-    static size_t attr_tc = 0;
-    if (smem_tc > attr_tc) {
+    static std::atomic<size_t> attr_tc[64];  // largest opt-in so far, per device ordinal (the attribute is per device)
+    int dev = 0;
+    LLB_CUDA(cudaGetDevice(&dev));
+    if (smem_tc > attr_tc[dev & 63].load(std::memory_order_acquire)) {
       LLB_CUDA(cudaFuncSetAttribute(t5_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_tc)));
-      attr_tc = smem_tc;
+      attr_tc[dev & 63].store(smem_tc, std::memory_order_release);
     }
     CUtensorMap tm;
     int rc = make_tmap_2d_bf16(&tm, qkv, static_cast<uint64_t>(batch) * rows_per_seq, static_cast<uint64_t>(3) * n_heads * kT5D,

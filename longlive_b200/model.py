@@ -398,6 +398,11 @@ class CausalWanModel(nn.Module):
         L = F * fs
         assert seq_len is None or L <= seq_len
         assert current_start % fs == 0, "current_start must be frame aligned"
+        if current_start // fs + F > ops.ROPE_MAX_POS or H // 2 > ops.ROPE_MAX_POS or W // 2 > ops.ROPE_MAX_POS:
+            # the reference's freqs table has 1024 positions per axis (causal_model.py:622-629) and its
+            # causal_rope_apply fails on a short slice beyond it (:46-52)
+            raise ValueError(f"RoPE position {current_start // fs + F} frames / grid {H // 2}x{W // 2} exceeds the "
+                             f"{ops.ROPE_MAX_POS}-position table")
         b = self._workspace_for(B, F, H, W, x.device)
 
         # --- integer bookkeeping (host only; replaces the reference's .item() round trips)

@@ -24,6 +24,9 @@ __all__ = [
 ]
 
 
+ROPE_MAX_POS = 1024  # LLB_ROPE_MAX_POS (include/llb200.h): rows of the (cos, sin) table per axis
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -332,7 +332,7 @@ class WanTextEncoder(nn.Module):
             if not os.path.exists(path):
                 raise FileNotFoundError(f"umT5 checkpoint {path} not found; pass text_encoder=UMT5Encoder(...)")
             text_encoder = UMT5Encoder()
-            text_encoder.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+            text_encoder.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
             text_encoder = text_encoder.to(torch.bfloat16)
             if torch.cuda.is_available():
                 text_encoder = text_encoder.cuda()

@@ -119,6 +119,10 @@ class UlyssesCausalWanModel(CausalWanModel):
         rows = slice(0, Lp)
         hw = self.hp * 128
         v = self.attn_variant
+        # Layer 0 stores K / V straight into the PEERS' rings before the first in-forward barrier.  A peer may still
+        # be zeroing its ring slices (allocate_kv_cache, the recache reset of a prompt switch) when a faster rank
+        # gets here, so every forward starts with a barrier: no remote store can precede a rank's local zeroing.
+        self._barrier()
         # embeddings: every rank patchifies the (replicated) input, then works on its own rows
         ops.patchify(b["x_in"][0], out=b["patches"][:L])
         x, xm = b["x"][rows], b["xm"][rows]

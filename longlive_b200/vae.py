@@ -291,6 +291,9 @@ class WanVAEDecoder(nn.Module):
     def _ring(self, key: str, frames: int, H: int, W: int, Cp: int, device) -> FrameRing:
         r = self._rings.get(key)
         if r is None or r.buf.shape != (frames, H, W, Cp) or r.buf.device != torch.device(device):
+            if r is not None:
+                # a captured graph bakes in the old buffer's address: decoding at another resolution drops them
+                self._graphs.clear()
             r = FrameRing(frames, H, W, Cp, device)
             self._rings[key] = r
         return r
@@ -300,6 +303,8 @@ class WanVAEDecoder(nn.Module):
         buffer, so its padding stays zero for the life of the decoder."""
         b = self._scratch.get(key)
         if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype or b.device != torch.device(device):
+            if b is not None:
+                self._graphs.clear()  # same reason as in _ring
             b = torch.zeros(shape, dtype=dtype, device=device)
             self._scratch[key] = b
         return b
