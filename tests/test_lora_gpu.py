@@ -1,0 +1,72 @@
+"""SURVEY 8f rank 1 on the GPU: LoRA merged into dense weights (longlive_b200.checkpoint.merge_lora) and
+run through the CUDA path vs the reference's way of running it - UNMERGED, y = W x + (alpha/r) B (A x) with
+every op rounded to bf16 (peft LoraLayer around each nn.Linear of the attention blocks,
+utils/lora_utils.py:19-75, inference.py:100-130) - evaluated by the oracle.
+
+Full-width model (dim 1536, 12 heads, FFN 8960), 2 blocks, rank 256 = alpha (configs/longlive_inference.yaml
+adapter section) on all 10 Linears of every block, adapter weights sized so that the LoRA delta is about half
+the base weight's magnitude.  Merging rounds W' = W + (alpha/r) B A once instead of adding two bf16 GEMM
+outputs, so the result is not bit-identical: the measured distance is printed and gated."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GATE = 8e-3   # flow prediction rel-L2, merged CUDA path vs unmerged bf16 oracle (lands at ~3e-3)
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def test_merged_lora_cuda_path_vs_unmerged_bf16_oracle():
+    from oracle import wan_oracle as wo
+    from longlive_b200.checkpoint import load_generator_weights
+    from longlive_b200.model import CausalWanModel
+    cfg = wo.WanConfig(num_layers=2)
+    fs = cfg.frame_seqlen
+    sd = wo.init_state_dict(cfg, seed=0)
+    r, alpha = 256, 256.0
+    g = torch.Generator().manual_seed(9)
+    lora_sd, lora_oracle = {}, {}
+    for i in range(cfg.num_layers):
+        for mod in ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k",
+                    "cross_attn.v", "cross_attn.o", "ffn.0", "ffn.2"):
+            name = f"blocks.{i}.{mod}"
+            out_f, in_f = sd[name + ".weight"].shape
+            A = (torch.randn(r, in_f, generator=g) * 0.03).to(torch.bfloat16)
+            B = (torch.randn(out_f, r, generator=g) * 0.03).to(torch.bfloat16)
+            # peft key style of a saved adapter (get_peft_model_state_dict)
+            lora_sd[f"base_model.model.{name}.lora_A.weight"] = A
+            lora_sd[f"base_model.model.{name}.lora_B.weight"] = B
+            lora_oracle[name] = (A.to(DEV), B.to(DEV), alpha / r)
+    delta = (lora_oracle["blocks.0.ffn.0"][1].float() @ lora_oracle["blocks.0.ffn.0"][0].float()) * (alpha / r)
+    ratio = (delta.norm() / sd["blocks.0.ffn.0.weight"].float().norm()).item()
+    assert 0.2 < ratio < 2.0, ratio  # the adapter really changes the weights
+
+    model = CausalWanModel(num_layers=2, local_attn_size=12, sink_size=3)
+    load_generator_weights(model, {"generator": {"model." + k: v for k, v in sd.items()}},
+                           lora={"generator_lora": lora_sd}, lora_alpha=alpha, lora_rank=r)
+    model = model.to(DEV).to(torch.bfloat16)
+    oracle = wo.OracleModel(cfg, sd, lora=lora_oracle).to(DEV)
+    plain = wo.OracleModel(cfg, sd).to(DEV)   # without the adapter: shows that the adapter matters
+
+    size = cfg.local_attn_size * fs
+    kv, cc = wo.new_kv_cache(cfg, 1, size, DEV), wo.new_crossattn_cache(cfg, 1, DEV)
+    okv, occ = wo.new_kv_cache(cfg, 1, size, DEV), wo.new_crossattn_cache(cfg, 1, DEV)
+    pkv, pcc = wo.new_kv_cache(cfg, 1, size, DEV), wo.new_crossattn_cache(cfg, 1, DEV)
+    ctx = wo.synth_prompt_embeds(cfg, 100, 150).to(DEV)
+    gi = torch.Generator().manual_seed(10)
+    errs, moved = [], []
+    for start, t in ((0, 1000.0), (0, 0.0), (3, 937.5), (3, 0.0), (6, 833.3333)):
+        x = torch.randn(1, 16, 3, 60, 104, generator=gi).to(torch.bfloat16).to(DEV)
+        tt = torch.full((1, 3), t, device=DEV)
+        a = model(x, t=tt, context=ctx, kv_cache=kv, crossattn_cache=cc, current_start=start * fs)
+        b = oracle.forward(x, tt, ctx, okv, occ, start * fs)
+        c = plain.forward(x, tt, ctx, pkv, pcc, start * fs)
+        errs.append(rel_l2(a, b)); moved.append(rel_l2(c, b))
+    print("merged-LoRA CUDA path vs unmerged bf16 oracle, flow rel-L2 per forward:", [f"{e:.2e}" for e in errs],
+          "| base model without adapter vs with:", [f"{e:.2e}" for e in moved])
+    assert max(errs) < GATE, errs
+    assert min(moved) > 3 * max(errs), (moved, errs)
