@@ -118,8 +118,10 @@ class CpuReference:
         self.model = None
         if ref_shims.shipped_available():
             try:
+                import contextlib
                 ref_shims.use_shipped_copy()
-                self.model = ref_shims.build_reference_model(cfg, sd, "fallback")
+                with contextlib.redirect_stdout(sys.stderr):  # the reference prints at import; stdout carries ONE JSON line
+                    self.model = ref_shims.build_reference_model(cfg, sd, "fallback")
                 self.kind = "reference"
             except Exception as e:  # e.g. an import the box cannot satisfy: fall back to the port, say so
                 print(f"[bench] reference tree not importable on this box ({e}); timing the oracle port", file=sys.stderr)
@@ -207,9 +209,10 @@ def reference_gpu_sample(torch, dev, pipe_args):
     import contextlib
     ref_shims.use_shipped_copy()
     cfg = wo.WanConfig()
-    wrapper = ref_shims.build_reference_wrapper(cfg, wo.init_state_dict(cfg, seed=0), shift=5.0,
-                                                attention_impl="flash", device=dev)
-    RefPipe, _ = ref_shims.reference_pipelines()
+    with contextlib.redirect_stdout(sys.stderr):  # the reference prints at import; stdout carries ONE JSON line
+        wrapper = ref_shims.build_reference_wrapper(cfg, wo.init_state_dict(cfg, seed=0), shift=5.0,
+                                                    attention_impl="flash", device=dev)
+        RefPipe, _ = ref_shims.reference_pipelines()
     prompt = wo.synth_prompt_embeds(cfg, 100, 200).to(dev)
     from types import SimpleNamespace
     vae = SimpleNamespace(decode_to_pixel=lambda latent, use_cache=False: latent.float())

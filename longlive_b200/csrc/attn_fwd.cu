@@ -17,8 +17,11 @@
 //   warp  8     MMA issuer (one thread): S_t = Q_t K_j^T, O_t += P_t V_j via tcgen05.mma
 //   warp  9     TMA producer: Q tiles once, then K_0,V_0,K_1,V_1,... through a shared-memory ring
 // TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each.  P (bf16) overwrites the first 64
-// columns of its S tile and is consumed straight from TMEM as the A operand of the PV MMA
-// (kPTmem = true); the kPTmem = false variant stages P through swizzled shared memory instead.
+// columns of its S tile and is consumed straight from TMEM as the A operand of the PV MMA.
+// (Round-1 experiments that measured slower - P staged through shared memory with an early-QK schedule,
+// a 64-key half-tile pipeline, two softmax warpgroups per Q tile, MUFU-only exp2 - and the compile-time
+// timing instrumentation were removed from the shipped kernel; DESIGN.md 4.1 keeps their numbers, the
+// history keeps their code.)
 // While the softmax warps of one Q tile work on S_t(j), the tensor core runs the other tile's
 // PV(j-1) and QK(j), so exp2/max/sum overlap with MMA issue.
 // Online softmax uses lazy rescaling: O is only rescaled (in TMEM, by the softmax warps) when the
@@ -41,51 +44,22 @@
 #include <stdlib.h>
 #include <string.h>
 
-// Timing experiments only (tools/attn_debug_sweep.py builds one library per value; results are garbage when != 0):
-// 1 no K/V TMA after the first ring fill, 2 no QK MMAs, 4 no PV MMAs, 8 no exp2, 16 no row max, 32 no S read from
-// TMEM, 64 no P write to TMEM, 128 no softmax arithmetic at all.  The shipped library is built with 0.
-#ifndef LLB_ATTN_DBG
-#define LLB_ATTN_DBG 0
-#endif
 
 namespace llb {
 
-constexpr int kDbg = LLB_ATTN_DBG;
-#if (LLB_ATTN_DBG & 2048)
-// 2048: CTA 0 time-stamps its hand-offs (clock64, first kTsSteps key tiles): [0] WG0 sees S ready, [1] WG0 hands P over,
-// [2] MMA warp sees P_0, [3] MMA warp has issued PV_0 + QK_0, [4] MMA warp sees P_1, [5] has issued PV_1 + QK_1,
-// [6] WG1 sees S ready, [7] WG1 hands P over
-constexpr int kTsSteps = 512;
-__device__ long long g_attn_ts[12][kTsSteps];  // [8] S in registers, [9] row max known, [10] all exp2 / P stores issued, [11] wait::st done (WG0)
-#define LLB_TS(slot, idx)                                                              \
-  do {                                                                                  \
-    if (blockIdx.x == 0 && lane == 0 && (idx) < kTsSteps) g_attn_ts[slot][idx] = clock64(); \
-  } while (0)
-#else
-#define LLB_TS(slot, idx) do { } while (0)
-#endif
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
 constexpr int kMinSplitTiles = 16;  // stream-K only when an item has at least this many kv tiles
+constexpr int kStages = 5;          // K/V tiles in flight
+constexpr int kPoly = 4;            // every 4th probability pair goes through the FMA-pipe polynomial exp2
+constexpr int kAttnSmemBytes = 1024 + 2 * kTileBytes + kStages * kTileBytes + 256;
 
 // workspace per CTA: partial O [2 tiles][32 col4][128 rows] float4, (m,l) [2][128] float2, flags [2][128]
 constexpr int64_t kWsOBytes = 2ll * 32 * 128 * 16;
 constexpr int64_t kWsMlBytes = 2ll * 128 * 8;
 constexpr int64_t kWsFlagBytes = 2ll * 128 * 4;
 constexpr int64_t kWsPerCta = kWsOBytes + kWsMlBytes + kWsFlagBytes;
-
-// kWide: two softmax warpgroups per Q tile (640 threads): each thread owns half a row (64 of the 128 key columns), the
-// row maximum is exchanged through shared memory; one K/V stage less makes room for the exchange buffer.
-template <bool kPTmem, bool kWide = false>
-struct AttnCfg {
-  static constexpr int kStages = kPTmem ? (kWide ? 4 : 5) : 3;
-  static constexpr int kThreads = kWide ? 640 : kAttnThreads;
-  static constexpr int kSoftmaxWarps = kWide ? 16 : 8;
-  static constexpr int kXchgBytes = kWide ? 2 * 2 * 2 * 128 * 4 : 0;  // [tile][half][buffer][row] float
-  static constexpr int kSmemBytes =
-      1024 + 2 * kTileBytes + (kPTmem ? 0 : 2 * kTileBytes) + kStages * kTileBytes + 256 + kXchgBytes;
-};
 
 struct AttnParams {
   __nv_bfloat16* out;
@@ -256,30 +230,22 @@ struct SegIter {
   }
 };
 
-// kPoly: every kPoly-th pair of probabilities is exponentiated with exp2_poly2 instead of MUFU
-// (0 = MUFU only).  MUFU.EX2 runs at 16/clk/SM, exactly the rate the two S tiles are produced at, so
-// moving a quarter of the work to the FMA pipe takes the special-function unit off the critical path.
-// kHalf (TMEM-P only): every 128-key tile is processed as two 64-key halves A | B with their own S buffers
-// (columns [0,64) and [64,128) of the tile's S region, P_h over the first 32 columns of S_h) and their own
-// barriers.  QK_B is issued right behind QK_A, and the next tile's QK_A right behind PV_A, so while a softmax
-// warpgroup works on one half the tensor core already refills the other: the per-Q-tile chain
-// QK -> softmax -> PV that bounds the whole-tile schedule is cut in two overlapping chains per Q tile.
-template <bool kPTmem, int kPoly, bool kHalf, bool kWide = false>
-__global__ void __maxnreg__((kWide ? 96 : 168))  // = 65536 / threads, rounded down to the allocation unit
+// kOpt ("optimistic exponent"): with lazy rescaling the exponent offset of tile j is, in the common case, the
+// running maximum left by tile j-1, so the exponentials do not have to wait for tile j's own row maximum.  The
+// kOpt softmax loop exponentiates S_t(j) against the OLD maximum while it scans for the new one in the same pass
+// and only redoes the tile (after rescaling O) in the rare case that the maximum grew by more than 2^8; the
+// ~300-cycle max phase leaves the QK -> softmax -> PV chain that bounds this kernel.
+template <bool kOpt>
+__global__ void __maxnreg__(168)  // = 65536 / 384 threads, rounded down to the allocation unit
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using Cfg = AttnCfg<kPTmem, kWide>;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kMmaWarp = Cfg::kSoftmaxWarps, kTmaWarp = Cfg::kSoftmaxWarps + 1;
-  static_assert(!kWide || (kPTmem && !kHalf), "kWide is built on the whole-tile TMEM-P schedule");
+  constexpr int kMmaWarp = 8, kTmaWarp = 9;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t q_base = smem_base;                                   // 2 tiles
-  const uint32_t p_base = q_base + 2 * kTileBytes;                     // 2 tiles (smem-P only)
-  const uint32_t kv_base = p_base + (kPTmem ? 0 : 2 * kTileBytes);     // kStages tiles
+  const uint32_t kv_base = q_base + 2 * kTileBytes;                    // kStages tiles
   const uint32_t bar_base = kv_base + kStages * kTileBytes;
-  uint8_t* p_gen = smem_gen + 2 * kTileBytes;
   uint8_t* bar_gen = smem_gen + (bar_base - smem_base);
   auto qfull_bar = [&](int s) { return bar_base + 8u * s; };
   auto qempty_bar = [&](int s) { return bar_base + 8u * (2 + s); };
@@ -289,14 +255,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto ofree_bar = [&](int s) { return bar_base + 8u * (10 + s); };
   auto kvfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
   auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
-  auto sfree_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };
-  auto phalf_bar = sfree_bar;  // TMEM-P path (no s_free there): first half of P_t(j) is in TMEM
-  auto sfullb_bar = [&](int s) { return bar_base + 8u * (15 + 2 * kStages + s); };  // kHalf: S_t half B ready
-  auto oadone_bar = [&](int s) { return bar_base + 8u * (17 + 2 * kStages + s); };  // kHalf: PV_t half A complete
+  auto phalf_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };  // first half of P_t(j) is in TMEM
   const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
-  [[maybe_unused]] float* xchg = reinterpret_cast<float*>(bar_gen + 256);  // kWide: row-max / row-sum exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -309,12 +271,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(qfull_bar(s), 1);
       mbar_init(qempty_bar(s), 1);
       mbar_init(sfull_bar(s), 1);
-      mbar_init(pfull_bar(s), kWide ? 8 : 4);  // one arrive per softmax warp
+      mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
-      mbar_init(ofree_bar(s), kWide ? 8 : 4);
-      mbar_init(sfree_bar(s), 4);
-      mbar_init(sfullb_bar(s), 1);
-      mbar_init(oadone_bar(s), 1);
+      mbar_init(ofree_bar(s), 4);
+      mbar_init(phalf_bar(s), 4);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
@@ -347,11 +307,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // warpgroups hold a full 128-column S row per thread and take 208, the MMA/TMA warpgroup keeps 88
   // ((168-88)*128 registers released >= (208-168)*256 requested, so the inc never blocks).
   if (warp >= kMmaWarp) {
-    // kWide: 640 threads launch at 96 registers; this warpgroup gives back (96-64)*128 = 4096, exactly the
-    // (104-96)*512 the four softmax warpgroups ask for (setmaxnreg.inc only draws on what the CTA itself released;
-    // 576 threads at 112 registers do not launch: warps are allocated four at a time)
-    if constexpr (kWide) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == kTmaWarp) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {
@@ -359,7 +315,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         uint32_t qph0 = 0, qph1 = 0;
-        [[maybe_unused]] int dbg_loaded = 0;
         for (; sg.ok; sg.next()) {
           const int head = sg.item / p.n_pairs;
           const int q_row0 = (sg.item - head * p.n_pairs) * 256;
@@ -381,648 +336,159 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           auto load_tile = [&](const CUtensorMap* tm, int row0) {
             mbar_wait(kvempty_bar(stage), phase ^ 1);
             const uint32_t dst = kv_base + stage * kTileBytes;
-            if ((kDbg & 1) && dbg_loaded >= kStages) {
-              mbar_arrive(kvfull_bar(stage));
-            } else {
-              mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
-              tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
-              tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
-              if (kDbg & 1) ++dbg_loaded;
-            }
+            mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
+            tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
+            tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           };
           kv_it.seek(sg.t0);
           int row0, valid;
-          if constexpr (kPTmem) {
-            // consumption order K_j, V_j, K_j+1, V_j+1, ...
-            for (int j = sg.t0; j < sg.t1; ++j) {
-              kv_it.get(row0, valid);
-              load_tile(&tmap_k, row0);
-              load_tile(&tmap_v, row0);
-              kv_it.next();
-            }
-          } else {
-            // early-QK order: K_t0, then (K_j+1, V_j) pairs - S(j+1) is produced before P(j) is consumed
-            KvTileIter k_it = kv_it;
-            k_it.get(row0, valid);
+          // consumption order K_j, V_j, K_j+1, V_j+1, ...
+          for (int j = sg.t0; j < sg.t1; ++j) {
+            kv_it.get(row0, valid);
             load_tile(&tmap_k, row0);
-            k_it.next();
-            for (int j = sg.t0; j < sg.t1; ++j) {
-              if (j + 1 < sg.t1) {
-                k_it.get(row0, valid);
-                load_tile(&tmap_k, row0);
-                k_it.next();
-              }
-              kv_it.get(row0, valid);
-              load_tile(&tmap_v, row0);
-              kv_it.next();
-            }
+            load_tile(&tmap_v, row0);
+            kv_it.next();
           }
         }
       }
     } else if (warp == kMmaWarp) {
       // ------------------------------------------------------------------ MMA issuer
       // The whole warp runs this loop (waits included); one elected lane issues the tcgen05 ops.
-      {
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(128, (kDbg & 256) ? 16 : 128, 0, 0);  // 256: same MMA count, 1/8 of the work
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(128, (kDbg & 256) ? 16 : 128, 0, 1);
-        auto issue_qk = [&](int t, uint32_t kst) {
-          if (kDbg & 2) return;
-          const uint32_t qa = q_base + t * kTileBytes;
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
+      auto issue_qk = [&](int t, uint32_t kst) {
+        const uint32_t qa = q_base + t * kTileBytes;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-            umma_ss(tmem_base + t * 128, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o),
-                    idesc_qk, kk != 0);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+          umma_ss(tmem_base + t * 128, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o),
+                  idesc_qk, kk != 0);
+        }
+      };
+      auto issue_pv = [&](int t, uint32_t vst, bool first, int kk0, int kk1) {
+#pragma unroll
+        for (int kk = kk0; kk < kk1; ++kk) {
+          // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA;
+          // A = P_t (bf16, 8 TMEM columns per 16 keys)
+          const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
+          umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bdesc, idesc_pv,
+                  (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      LLB_ATTN_INIT_WORK();
+      int stage = 0;
+      uint32_t phase = 0;
+      auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
+      uint32_t qph0 = 0, qph1 = 0;    // q_full consumer phases
+      uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
+      uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
+      for (; sg.ok; sg.next()) {
+        const int head = sg.item / p.n_pairs;
+        const int q_row0 = (sg.item - head * p.n_pairs) * 256;
+        const bool has1 = q_row0 + 128 < p.Lq;
+        const int nt = sg.t1 - sg.t0;
+        // prologue: S_t(first) = Q_t K^T
+        mbar_wait(qfull_bar(0), qph0);
+        qph0 ^= 1;
+        if (has1) {
+          mbar_wait(qfull_bar(1), qph1);
+          qph1 ^= 1;
+        }
+        mbar_wait(kvfull_bar(stage), phase);
+        tc_fence_after();
+        uint32_t kst = kv_base + stage * kTileBytes;
+        if (elect_one()) {
+          issue_qk(0, kst);
+          umma_commit(sfull_bar(0));
+          if (nt == 1) umma_commit(qempty_bar(0));
+          if (has1) {
+            issue_qk(1, kst);
+            umma_commit(sfull_bar(1));
+            if (nt == 1) umma_commit(qempty_bar(1));
           }
-        };
-        auto issue_pv = [&](int t, uint32_t vst, bool first, int kk0, int kk1) {
-          if (kDbg & 4) return;
-#pragma unroll
-          for (int kk = kk0; kk < kk1; ++kk) {
-            // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA
-            const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
-            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
-            if constexpr (kPTmem) {
-              umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, bdesc, idesc_pv, acc);
-            } else {
-              const uint32_t pa = p_base + t * kTileBytes + (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-              umma_ss(tmem_base + 256 + t * 128, umma_desc_kmajor(pa), bdesc, idesc_pv, acc);
-            }
-          }
-        };
-        LLB_ATTN_INIT_WORK();
-        int stage = 0;
-        uint32_t phase = 0;
-        auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
-        uint32_t qph0 = 0, qph1 = 0;    // q_full consumer phases
-        uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
-        uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
-
-        if constexpr (kPTmem && kHalf) {
-          constexpr uint32_t idesc_qk64 = umma_idesc_bf16(128, 64, 0, 0);
-          // S_t half h (64 keys): D = columns [h*64, h*64+64) of the tile's S region, B = key rows h*64.. of K
-          auto issue_qk_half = [&](int t, uint32_t kst, int h) {
-            const uint32_t qa = q_base + t * kTileBytes;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-              umma_ss(tmem_base + t * 128 + h * 64, umma_desc_kmajor(qa + o),
-                      umma_desc_kmajor(kst + h * 8192 + o), idesc_qk64, kk != 0);
-            }
-          };
-          // O_t += P_t half h (bf16 in the first 32 columns of S_t half h) x V rows h*64 .. h*64+63
-          auto issue_pv_half = [&](int t, uint32_t vst, bool first, int h) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t bdesc = umma_desc_mnmajor(vst + (h * 4 + kk) * 2048, kBoxBytes);
-              umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + h * 64 + kk * 8, bdesc, idesc_pv,
-                      (first && kk == 0) ? 0u : 1u);
-            }
-          };
-          for (; sg.ok; sg.next()) {
-            const int head = sg.item / p.n_pairs;
-            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-            const bool has1 = q_row0 + 128 < p.Lq;
-            const int nt = sg.t1 - sg.t0;
-            mbar_wait(qfull_bar(0), qph0);
-            qph0 ^= 1;
-            if (has1) {
-              mbar_wait(qfull_bar(1), qph1);
-              qph1 ^= 1;
-            }
+          umma_commit(kvempty_bar(stage));
+        }
+        __syncwarp();
+        advance();
+        // O_t of the previous segment must have been drained by its softmax warps before the
+        // first PV of this segment overwrites it
+        mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
+        oseg0++;
+        if (has1) {
+          mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
+          oseg1++;
+        }
+        for (int j = 0; j < nt; ++j) {
+          const bool more = j + 1 < nt;
+          const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
+          // V_j
+          const int vstage = stage;
+          mbar_wait(kvfull_bar(stage), phase);
+          const uint32_t vst = kv_base + stage * kTileBytes;
+          advance();
+          // K_{j+1}
+          int kstage = 0;
+          if (more) {
+            kstage = stage;
             mbar_wait(kvfull_bar(stage), phase);
-            tc_fence_after();
-            uint32_t kst = kv_base + stage * kTileBytes;
-            if (elect_one()) {
-              issue_qk_half(0, kst, 0);
-              umma_commit(sfull_bar(0));
-              if (has1) {
-                issue_qk_half(1, kst, 0);
-                umma_commit(sfull_bar(1));
-              }
-              issue_qk_half(0, kst, 1);
-              umma_commit(sfullb_bar(0));
-              if (nt == 1) umma_commit(qempty_bar(0));
-              if (has1) {
-                issue_qk_half(1, kst, 1);
-                umma_commit(sfullb_bar(1));
-                if (nt == 1) umma_commit(qempty_bar(1));
-              }
-              umma_commit(kvempty_bar(stage));
-            }
-            __syncwarp();
+            kst = kv_base + stage * kTileBytes;
             advance();
-            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
-            oseg0++;
-            if (has1) {
-              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
-              oseg1++;
-            }
-            for (int j = 0; j < nt; ++j) {
-              const bool more = j + 1 < nt;
-              const bool last_qk = j + 2 == nt;
-              const int vstage = stage;
-              mbar_wait(kvfull_bar(stage), phase);
-              const uint32_t vst = kv_base + stage * kTileBytes;
-              advance();
-              int kstage = 0;
-              if (more) {
-                kstage = stage;
-                mbar_wait(kvfull_bar(stage), phase);
-                kst = kv_base + stage * kTileBytes;
-                advance();
-              }
-              // half A of both tiles: O_t += P_tA(j) V_j[0:64]; S_tA(j+1) = Q_t K_{j+1}[0:64]^T
-              mbar_wait(phalf_bar(0), pcnt0 & 1);
-              tc_fence_after();
-              if (elect_one()) {
-                issue_pv_half(0, vst, j == 0, 0);
-                umma_commit(oadone_bar(0));
-                if (more) {
-                  issue_qk_half(0, kst, 0);
-                  umma_commit(sfull_bar(0));
-                }
-              }
-              __syncwarp();
-              if (has1) {
-                mbar_wait(phalf_bar(1), pcnt1 & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                  issue_pv_half(1, vst, j == 0, 0);
-                  umma_commit(oadone_bar(1));
-                  if (more) {
-                    issue_qk_half(1, kst, 0);
-                    umma_commit(sfull_bar(1));
-                  }
-                }
-                __syncwarp();
-              }
-              // half B
-              mbar_wait(pfull_bar(0), pcnt0 & 1);
-              pcnt0++;
-              tc_fence_after();
-              if (elect_one()) {
-                issue_pv_half(0, vst, false, 1);
-                umma_commit(odone_bar(0));
-                if (more) {
-                  issue_qk_half(0, kst, 1);
-                  umma_commit(sfullb_bar(0));
-                  if (last_qk) umma_commit(qempty_bar(0));
-                }
-                if (!has1) {
-                  umma_commit(kvempty_bar(vstage));
-                  if (more) umma_commit(kvempty_bar(kstage));
-                }
-              }
-              __syncwarp();
-              if (has1) {
-                mbar_wait(pfull_bar(1), pcnt1 & 1);
-                pcnt1++;
-                tc_fence_after();
-                if (elect_one()) {
-                  issue_pv_half(1, vst, false, 1);
-                  umma_commit(odone_bar(1));
-                  umma_commit(kvempty_bar(vstage));
-                  if (more) {
-                    issue_qk_half(1, kst, 1);
-                    umma_commit(sfullb_bar(1));
-                    if (last_qk) umma_commit(qempty_bar(1));
-                    umma_commit(kvempty_bar(kstage));
-                  }
-                }
-                __syncwarp();
-              }
-            }
           }
-        } else if constexpr (kPTmem) {
-          for (; sg.ok; sg.next()) {
-            const int head = sg.item / p.n_pairs;
-            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-            const bool has1 = q_row0 + 128 < p.Lq;
-            const int nt = sg.t1 - sg.t0;
-            // prologue: S_t(first) = Q_t K^T
-            mbar_wait(qfull_bar(0), qph0);
-            qph0 ^= 1;
-            if (has1) {
-              mbar_wait(qfull_bar(1), qph1);
-              qph1 ^= 1;
-            }
-            mbar_wait(kvfull_bar(stage), phase);
+          // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
+          // (split: the first 64 keys of P_0(j) arrive while the softmax warps still exponentiate the rest)
+          if (p.split_p) {
+            mbar_wait(phalf_bar(0), pcnt0 & 1);
             tc_fence_after();
-            uint32_t kst = kv_base + stage * kTileBytes;
-            if (elect_one()) {
+            if (elect_one()) issue_pv(0, vst, j == 0, 0, 4);
+            __syncwarp();
+          }
+          mbar_wait(pfull_bar(0), pcnt0 & 1);
+          pcnt0++;
+          tc_fence_after();
+          if (elect_one()) {
+            if (p.split_p) issue_pv(0, vst, false, 4, 8);
+            else issue_pv(0, vst, j == 0, 0, 8);
+            umma_commit(odone_bar(0));
+            if (more) {
               issue_qk(0, kst);
               umma_commit(sfull_bar(0));
-              if (nt == 1) umma_commit(qempty_bar(0));
-              if (has1) {
-                issue_qk(1, kst);
-                umma_commit(sfull_bar(1));
-                if (nt == 1) umma_commit(qempty_bar(1));
-              }
-              umma_commit(kvempty_bar(stage));
+              if (last_qk) umma_commit(qempty_bar(0));
             }
-            __syncwarp();
-            advance();
-            // O_t of the previous segment must have been drained by its softmax warps before the
-            // first PV of this segment overwrites it
-            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
-            oseg0++;
-            if (has1) {
-              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
-              oseg1++;
-            }
-            for (int j = 0; j < nt; ++j) {
-              const bool more = j + 1 < nt;
-              const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
-              // V_j
-              const int vstage = stage;
-              mbar_wait(kvfull_bar(stage), phase);
-              const uint32_t vst = kv_base + stage * kTileBytes;
-              advance();
-              // K_{j+1}
-              int kstage = 0;
-              if (more) {
-                kstage = stage;
-                mbar_wait(kvfull_bar(stage), phase);
-                kst = kv_base + stage * kTileBytes;
-                advance();
-              }
-              // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
-              // (split: the first 64 keys of P_0(j) arrive while the softmax warps still exponentiate the rest)
-              if (p.split_p) {
-                mbar_wait(phalf_bar(0), pcnt0 & 1);
-                tc_fence_after();
-                if (elect_one()) issue_pv(0, vst, j == 0, 0, 4);
-                __syncwarp();
-              }
-              mbar_wait(pfull_bar(0), pcnt0 & 1);
-              LLB_TS(2, pcnt0);
-              pcnt0++;
-              tc_fence_after();
-              if (elect_one()) {
-                if (p.split_p) issue_pv(0, vst, false, 4, 8);
-                else issue_pv(0, vst, j == 0, 0, 8);
-                if (!(kDbg & 512) || !more) umma_commit(odone_bar(0));
-                if (more) {
-                  issue_qk(0, kst);
-                  umma_commit(sfull_bar(0));
-                  if (last_qk) umma_commit(qempty_bar(0));
-                }
-                if (!has1) {
-                  umma_commit(kvempty_bar(vstage));
-                  if (more) umma_commit(kvempty_bar(kstage));
-                }
-              }
-              __syncwarp();
-              LLB_TS(3, pcnt0 - 1);
-              if (has1) {
-                if (p.split_p) {
-                  mbar_wait(phalf_bar(1), pcnt1 & 1);
-                  tc_fence_after();
-                  if (elect_one()) issue_pv(1, vst, j == 0, 0, 4);
-                  __syncwarp();
-                }
-                mbar_wait(pfull_bar(1), pcnt1 & 1);
-                LLB_TS(4, pcnt1);
-                pcnt1++;
-                tc_fence_after();
-                if (elect_one()) {
-                  if (p.split_p) issue_pv(1, vst, false, 4, 8);
-                  else issue_pv(1, vst, j == 0, 0, 8);
-                  if (!(kDbg & 512) || !more) umma_commit(odone_bar(1));
-                  umma_commit(kvempty_bar(vstage));
-                  if (more) {
-                    issue_qk(1, kst);
-                    umma_commit(sfull_bar(1));
-                    if (last_qk) umma_commit(qempty_bar(1));
-                    umma_commit(kvempty_bar(kstage));
-                  }
-                }
-                __syncwarp();
-                LLB_TS(5, pcnt1 - 1);
-              }
+            if (!has1) {
+              umma_commit(kvempty_bar(vstage));
+              if (more) umma_commit(kvempty_bar(kstage));
             }
           }
-        } else {
-          // Early-QK schedule (P staged in shared memory, so S and P do not alias): S_t(j+1) = Q_t K_j+1^T
-          // is issued as soon as the softmax warps have READ S_t(j) (s_free), before P_t(j) exists.
-          // The softmax warpgroups then find their next S tile ready and run back to back.
-          uint32_t qk0 = 0, qk1 = 0;  // QK groups issued per Q tile (s_free phase)
-          for (; sg.ok; sg.next()) {
-            const int head = sg.item / p.n_pairs;
-            const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-            const bool has1 = q_row0 + 128 < p.Lq;
-            const int nt = sg.t1 - sg.t0;
-            mbar_wait(qfull_bar(0), qph0);
-            qph0 ^= 1;
-            if (has1) {
-              mbar_wait(qfull_bar(1), qph1);
-              qph1 ^= 1;
+          __syncwarp();
+          if (has1) {
+            if (p.split_p) {
+              mbar_wait(phalf_bar(1), pcnt1 & 1);
+              tc_fence_after();
+              if (elect_one()) issue_pv(1, vst, j == 0, 0, 4);
+              __syncwarp();
             }
-            mbar_wait(kvfull_bar(stage), phase);
-            // S_t must have been read by the softmax warps of the previous segment's last tile
-            if (qk0 > 0) mbar_wait(sfree_bar(0), (qk0 - 1) & 1);
-            if (has1 && qk1 > 0) mbar_wait(sfree_bar(1), (qk1 - 1) & 1);
+            mbar_wait(pfull_bar(1), pcnt1 & 1);
+            pcnt1++;
             tc_fence_after();
-            uint32_t kst = kv_base + stage * kTileBytes;
             if (elect_one()) {
-              issue_qk(0, kst);
-              umma_commit(sfull_bar(0));
-              if (nt == 1) umma_commit(qempty_bar(0));
-              if (has1) {
+              if (p.split_p) issue_pv(1, vst, false, 4, 8);
+              else issue_pv(1, vst, j == 0, 0, 8);
+              umma_commit(odone_bar(1));
+              umma_commit(kvempty_bar(vstage));
+              if (more) {
                 issue_qk(1, kst);
                 umma_commit(sfull_bar(1));
-                if (nt == 1) umma_commit(qempty_bar(1));
+                if (last_qk) umma_commit(qempty_bar(1));
+                umma_commit(kvempty_bar(kstage));
               }
-              umma_commit(kvempty_bar(stage));
             }
             __syncwarp();
-            qk0++;
-            if (has1) qk1++;
-            advance();
-            mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
-            oseg0++;
-            if (has1) {
-              mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
-              oseg1++;
-            }
-            for (int j = 0; j < nt; ++j) {
-              const bool more = j + 1 < nt;
-              const bool last_qk = j + 2 == nt;
-              if (more) {
-                // K_{j+1}: S_t(j+1) as soon as S_t(j) has been read
-                const int kstage = stage;
-                mbar_wait(kvfull_bar(stage), phase);
-                kst = kv_base + stage * kTileBytes;
-                advance();
-                mbar_wait(sfree_bar(0), (qk0 - 1) & 1);
-                qk0++;
-                tc_fence_after();
-                if (elect_one()) {
-                  issue_qk(0, kst);
-                  umma_commit(sfull_bar(0));
-                  if (last_qk) umma_commit(qempty_bar(0));
-                  if (!has1) umma_commit(kvempty_bar(kstage));
-                }
-                __syncwarp();
-                if (has1) {
-                  mbar_wait(sfree_bar(1), (qk1 - 1) & 1);
-                  qk1++;
-                  tc_fence_after();
-                  if (elect_one()) {
-                    issue_qk(1, kst);
-                    umma_commit(sfull_bar(1));
-                    if (last_qk) umma_commit(qempty_bar(1));
-                    umma_commit(kvempty_bar(kstage));
-                  }
-                  __syncwarp();
-                }
-              }
-              // V_j: O_t += P_t(j) V_j
-              const int vstage = stage;
-              mbar_wait(kvfull_bar(stage), phase);
-              const uint32_t vst = kv_base + stage * kTileBytes;
-              advance();
-              mbar_wait(pfull_bar(0), pcnt0 & 1);
-              pcnt0++;
-              tc_fence_after();
-              if (elect_one()) {
-                issue_pv(0, vst, j == 0, 0, 8);
-                umma_commit(odone_bar(0));
-                if (!has1) umma_commit(kvempty_bar(vstage));
-              }
-              __syncwarp();
-              if (has1) {
-                mbar_wait(pfull_bar(1), pcnt1 & 1);
-                pcnt1++;
-                tc_fence_after();
-                if (elect_one()) {
-                  issue_pv(1, vst, j == 0, 0, 8);
-                  umma_commit(odone_bar(1));
-                  umma_commit(kvempty_bar(vstage));
-                }
-                __syncwarp();
-              }
-            }
           }
         }
       }
     }
   } else {
-    if constexpr (kWide) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    // -------------------------------------------------------------------- softmax warps, two warpgroups per Q tile
-    // warps 0-3 / 4-7: Q tile 0, key columns [0,64) / [64,128) of every key tile; warps 8-11 / 12-15: Q tile 1.
-    // Both warpgroups of a tile wait on the same s_full barrier; the thread pair of a row exchanges its half-row
-    // maximum through shared memory (named barrier 1 + t, 256 threads, buffers alternate per key tile), so both
-    // take the same rescale decision; each rescales / drains its own 64 columns of O_t.
-    const int t = warp >> 3;
-    const int hf = (warp >> 2) & 1;
-    const int q = warp & 3;
-    const int row_in_tile = q * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + t * 128;
-    const uint32_t t_o = tmem_base + lane_off + 256 + t * 128 + hf * 64;
-    const float c = p.scale_log2;
-    uint32_t cnt = 0;
-    const int64_t ws_row = static_cast<int64_t>(t) * 128 + row_in_tile;
-    float* x_own = xchg + ((t * 2 + hf) * 2) * 128 + row_in_tile;         // [buffer 0], +128 = buffer 1
-    const float* x_oth = xchg + ((t * 2 + (hf ^ 1)) * 2) * 128 + row_in_tile;
-    auto pair_sync = [&]() {
-      if (t == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 2, 256;" ::: "memory");
-    };
-    LLB_ATTN_INIT_WORK();
-
-    for (; sg.ok; sg.next()) {
-      const int head = sg.item / p.n_pairs;
-      const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-      const bool has1 = q_row0 + 128 < p.Lq;
-      if (t == 1 && !has1) continue;
-      const int grow = q_row0 + t * 128 + row_in_tile;
-      float m_used = -INFINITY;
-      float l = 0.f;  // sum over this thread's 64 columns only; the halves are added in the segment epilogue
-      kv_it.seek(sg.t0);
-      for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
-        int row0, valid;
-        kv_it.get(row0, valid);
-        const uint32_t buf = (cnt & 1) * 128;
-        mbar_wait(sfull_bar(t), cnt & 1);
-        cnt++;
-        tc_fence_after();
-        uint32_t sv[2][32];
-        tmem_ld32(t_s + hf * 64, sv[0]);
-        tmem_ld32(t_s + hf * 64 + 32, sv[1]);
-        tmem_wait_ld();
-        if (valid < hf * 64 + 64) {
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (hf * 64 + cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
-        }
-        x_own[buf] = fmaxf(mx0, mx1);
-        // also orders the partner's S reads before this thread's P stores (P overlays S columns [0,64))
-        pair_sync();
-        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), x_oth[buf]));
-        const bool need = (m_new - m_used) * c > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used = -inf)
-          if (j > sg.t0) {
-            // S_t(j) ready implies PV_t(j-1) complete (issued before QK_t(j)): O is stable.  16 columns at a time:
-            // the half row of S stays live across this (rare) path and the register budget is 112
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t ov[16];
-              tmem_ld16(t_o + cc * 16, ov);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
-              tmem_st16(t_o + cc * 16, ov);
-            }
-            tmem_wait_st();
-          }
-          l *= f;
-          m_used = m_new;
-        }
-        const float neg = -m_used * c;
-        const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
-        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 tt = __ffma2_rn(
-                make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
-            float2 pp;
-            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
-              pp = exp2_poly2(tt);
-            } else {
-              pp.x = ex2_approx(tt.x);
-              pp.y = ex2_approx(tt.y);
-            }
-            if (i & 1) lb = __fadd2_rn(lb, pp);
-            else la = __fadd2_rn(la, pp);
-            pk[i] = pack_bf16x2(pp.x, pp.y);
-          }
-          tmem_st16(t_s + hf * 32 + cc * 16, pk);  // P: keys hf*64 + cc*32 .. +31 -> 16 packed columns
-        }
-        la = __fadd2_rn(la, lb);
-        l += la.x + la.y;
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pfull_bar(t));
-      }
-      // ---- segment epilogue: each thread owns output columns [hf*64, hf*64 + 64) of its row
-      mbar_wait(odone_bar(t), (cnt - 1) & 1);
-      tc_fence_after();
-      x_own[0] = l;  // buffer 0 / 1 are both free here: the last exchange of the loop was read before pfull
-      pair_sync();
-      l += x_oth[0];
-      const bool tail_part = sg.in_remainder() && sg.t0 > 0;
-      const bool head_part = sg.in_remainder() && sg.t1 < sg.T;
-      const bool row_ok = grow < p.Lq;
-      float a_own = 1.0f, a_oth = 0.0f;
-      const float4* wo_in = nullptr;
-      uint32_t* flag_in = nullptr;
-      if (head_part && row_ok) {
-        uint8_t* wsb = p.workspace + static_cast<int64_t>(blockIdx.x + 1) * kWsPerCta;
-        flag_in = reinterpret_cast<uint32_t*>(wsb + kWsOBytes + kWsMlBytes) + ws_row;
-        uint32_t spins = 0;
-        uint64_t t_start = 0;
-        while (ld_acquire_u32(flag_in) == 0u) {
-          if ((++spins & 0xfffu) == 0) {
-            const uint64_t now = global_timer_ns();
-            if (t_start == 0) t_start = now;
-            else if (now - t_start > LLB_WAIT_TIMEOUT_NS) __trap();
-          }
-        }
-        const volatile float* mlp = reinterpret_cast<const volatile float*>(wsb + kWsOBytes) + 2 * ws_row;
-        const float m_oth = mlp[0], l_oth = mlp[1];
-        const float m = fmaxf(m_used, m_oth);
-        a_own = ex2_approx((m_used - m) * c);
-        a_oth = ex2_approx((m_oth - m) * c);
-        l = l * a_own + l_oth * a_oth;
-        m_used = m;
-        wo_in = reinterpret_cast<const float4*>(wsb) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
-      }
-      uint8_t* wsb_out = p.workspace + static_cast<int64_t>(blockIdx.x) * kWsPerCta;
-      float4* wo_out = reinterpret_cast<float4*>(wsb_out) + static_cast<int64_t>(t) * (32 * 128) + row_in_tile;
-      if (!tail_part) {
-        const float inv = 1.0f / l;
-        a_own *= inv;
-        a_oth *= inv;
-      }
-      __nv_bfloat16* orow = p.out + static_cast<int64_t>(grow) * p.ldo + head * 128;
-      if (p.shard.n_ranks > 1 && row_ok) {
-        const int r = grow / p.shard.rows_per_rank;
-        orow = static_cast<__nv_bfloat16*>(p.shard.out_peers[r]) +
-               static_cast<int64_t>(grow - r * p.shard.rows_per_rank) * p.shard.ld_out + p.shard.head_col0 +
-               head * 128;
-      }
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int col = hf * 64 + c4 * 16;  // first of 16 output columns
-        uint32_t ov[16];
-        tmem_ld16(t_o + c4 * 16, ov);
-        tmem_wait_ld();
-        if (row_ok) {
-          float o[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(ov[i]) * a_own;
-          if (wo_in != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 x = ld_cg_f4(wo_in + (col / 4 + i) * 128);
-              o[4 * i] += x.x * a_oth;
-              o[4 * i + 1] += x.y * a_oth;
-              o[4 * i + 2] += x.z * a_oth;
-              o[4 * i + 3] += x.w * a_oth;
-            }
-          }
-          if (tail_part) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              wo_out[(col / 4 + i) * 128] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint4 w;
-              w.x = pack_bf16x2(o[8 * i + 0], o[8 * i + 1]);
-              w.y = pack_bf16x2(o[8 * i + 2], o[8 * i + 3]);
-              w.z = pack_bf16x2(o[8 * i + 4], o[8 * i + 5]);
-              w.w = pack_bf16x2(o[8 * i + 6], o[8 * i + 7]);
-              *reinterpret_cast<uint4*>(orow + col + i * 8) = w;
-            }
-          }
-        }
-      }
-      // the flag of the merged partial is consumed, and our own partial published, by the hf == 0 thread of the
-      // row after BOTH halves are done with the workspace (their writes fenced, then the pair barrier)
-      if (tail_part) __threadfence();
-      pair_sync();
-      if (hf == 0) {
-        if (flag_in != nullptr) st_release_u32(flag_in, 0u);
-        if (tail_part && row_ok) {
-          reinterpret_cast<float2*>(wsb_out + kWsOBytes)[ws_row] = make_float2(m_used, l);
-          __threadfence();
-          st_release_u32(reinterpret_cast<uint32_t*>(wsb_out + kWsOBytes + kWsMlBytes) + ws_row, 1u);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ofree_bar(t));
-    }
-    } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // -------------------------------------------------------------------- softmax warps
     const int t = warp >> 2;  // Q tile handled by this warpgroup
@@ -1033,9 +499,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_o = tmem_base + lane_off + 256 + t * 128;
     const float c = p.scale_log2;
     uint32_t cnt = 0;  // kv tiles processed by this warpgroup (s_full / o_done phase)
-    [[maybe_unused]] uint32_t segcnt = 0;
     const int64_t ws_row = static_cast<int64_t>(t) * 128 + row_in_tile;
     LLB_ATTN_INIT_WORK();
+
+    // P chunk cc (keys cc*32 .. +31) = exp2(S * c + neg), packed to bf16 into TMEM columns [cc*16, cc*16+16) of
+    // the S tile; row sums of the fp32 probabilities accumulate in la / lb
+    auto exp_chunk = [&](const uint32_t (&s)[32], int cc, float2 c2, float2 neg2, float2& la, float2& lb) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 tt = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, neg2);
+        float2 pp;
+        if ((i % kPoly) == kPoly - 1) {
+          pp = exp2_poly2(tt);
+        } else {
+          pp.x = ex2_approx(tt.x);
+          pp.y = ex2_approx(tt.y);
+        }
+        if (i & 1) lb = __fadd2_rn(lb, pp);
+        else la = __fadd2_rn(la, pp);
+        pk[i] = pack_bf16x2(pp.x, pp.y);
+      }
+      tmem_st16(t_s + cc * 16, pk);
+    };
+    // O_t *= f (TMEM read-modify-write by the row's owner; O must be stable, see the call sites)
+    auto rescale_o = [&](float f) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t ov[32];
+        tmem_ld32(t_o + cc * 32, ov);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+        tmem_st32(t_o + cc * 32, ov);
+      }
+      tmem_wait_st();
+    };
 
     for (; sg.ok; sg.next()) {
       const int head = sg.item / p.n_pairs;
@@ -1049,109 +548,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
         int row0, valid;
         kv_it.get(row0, valid);
-        if constexpr (kPTmem && kHalf) {
-          const uint32_t ph = cnt & 1;
-          cnt++;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(h == 0 ? sfull_bar(t) : sfullb_bar(t), ph);
-            tc_fence_after();
-            uint32_t sv[2][32];
-            tmem_ld32(t_s + h * 64, sv[0]);
-            tmem_ld32(t_s + h * 64 + 32, sv[1]);
-            tmem_wait_ld();
-            if (valid < h * 64 + 64) {
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (h * 64 + cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-              mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
-            }
-            const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-            const bool need = (m_new - m_used) * c > 8.0f;
-            if (__any_sync(0xffffffffu, need)) {
-              const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first half (m_used = -inf)
-              if (j > sg.t0 || h == 1) {
-                // O must be stable: every PV issued so far for this Q tile has to be complete.  Before half A
-                // that is PV_B of the previous key tile, before half B it is PV_A of this one.
-                if (h == 0) mbar_wait(odone_bar(t), ph ^ 1);
-                else mbar_wait(oadone_bar(t), ph);
-                tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                  uint32_t ov[32];
-                  tmem_ld32(t_o + cc * 32, ov);
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
-                  tmem_st32(t_o + cc * 32, ov);
-                }
-                tmem_wait_st();
-              }
-              l *= f;
-              m_used = m_new;
-            }
-            const float neg = -m_used * c;
-            const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
-            float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float2 tt = __ffma2_rn(
-                    make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
-                float2 pp;
-                if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
-                  pp = exp2_poly2(tt);
-                } else {
-                  pp.x = ex2_approx(tt.x);
-                  pp.y = ex2_approx(tt.y);
-                }
-                if (i & 1) lb = __fadd2_rn(lb, pp);
-                else la = __fadd2_rn(la, pp);
-                pk[i] = pack_bf16x2(pp.x, pp.y);
-              }
-              tmem_st16(t_s + h * 64 + cc * 16, pk);
-            }
-            la = __fadd2_rn(la, lb);
-            l += la.x + la.y;
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(h == 0 ? phalf_bar(t) : pfull_bar(t));
-          }
-          continue;
-        }
         mbar_wait(sfull_bar(t), cnt & 1);
-        if (q == 0) LLB_TS(t == 0 ? 0 : 6, cnt);
         cnt++;
         tc_fence_after();
         uint32_t sv[4][32];
-        if constexpr ((kDbg & 32) != 0) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sv[cc][i] = __float_as_uint(static_cast<float>(j + i));
-        } else {
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
-          tmem_wait_ld();
-        }
-        if (q == 0 && t == 0) LLB_TS(8, cnt - 1);
-        bool prev_pv_done = kPTmem || j == sg.t0;  // TMEM-P: S_t(j) ready already implies PV_t(j-1) done
-        if constexpr (!kPTmem) {
-          // S_t(j) now lives in registers: let the MMA warp overwrite it with S_t(j+1)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sfree_bar(t));
-        }
+        for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
+        tmem_wait_ld();
         if (valid < 128) {
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
@@ -1159,10 +562,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int i = 0; i < 32; ++i)
               if (cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        if constexpr ((kDbg & 16) != 0) {
-          mx0 = __uint_as_float(sv[0][0]);
+        const float2 c2 = make_float2(c, c);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+        if (kOpt && j > sg.t0) {
+          // ---- optimistic pass: exponentiate against the maximum the previous tiles left while scanning for
+          // this tile's own maximum (one fused pass over the row)
+          const float neg_old = -m_used * c;
+          const float2 neg2 = make_float2(neg_old, neg_old);
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[cc][i]), __uint_as_float(sv[cc][i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[cc][i + 2]), __uint_as_float(sv[cc][i + 3])));
+              mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[cc][i + 4]), __uint_as_float(sv[cc][i + 5])));
+              mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[cc][i + 6]), __uint_as_float(sv[cc][i + 7])));
+            }
+            exp_chunk(sv[cc], cc, c2, neg2, la, lb);
+          }
+          const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+          const bool need = (m_new - m_used) * c > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare: the maximum grew by more than 2^8.  S_t(j) ready implies PV_t(j-1) complete (issued before
+            // QK_t(j)), so O is stable: rescale it, then redo this tile against the new maximum (S is still in
+            // registers; the P columns written above are simply overwritten)
+            tmem_wait_st();
+            const float f = ex2_approx((m_used - m_new) * c);
+            rescale_o(f);
+            l *= f;
+            m_used = m_new;
+            const float neg_new = -m_used * c;
+            const float2 neg2n = make_float2(neg_new, neg_new);
+            la = make_float2(0.f, 0.f);
+            lb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) exp_chunk(sv[cc], cc, c2, neg2n, la, lb);
+          }
         } else {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
@@ -1170,67 +608,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mx2 = fmaxf(mx2, __uint_as_float(sv[2][i]));
             mx3 = fmaxf(mx3, __uint_as_float(sv[3][i]));
           }
-        }
-        const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-        // lazy rescale: only when the max moved by more than 2^8 in the exp2 domain
-        const bool need = (m_new - m_used) * c > 8.0f;
-        if (__any_sync(0xffffffffu, need)) {
-          const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
-          if (j > sg.t0) {
-            // O must be stable: PV_t(j-1) complete (TMEM-P: implied by S_t(j); early-QK: wait for it)
-            if (!prev_pv_done) {
-              mbar_wait(odone_bar(t), (cnt - 2) & 1);
-              tc_fence_after();
-              prev_pv_done = true;
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t ov[32];
-              tmem_ld32(t_o + cc * 32, ov);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
-              tmem_st32(t_o + cc * 32, ov);
-            }
-            tmem_wait_st();
+          const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+          // lazy rescale: only when the max moved by more than 2^8 in the exp2 domain
+          const bool need = (m_new - m_used) * c > 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
+            // O must be stable: PV_t(j-1) complete, which S_t(j) being ready implies
+            if (j > sg.t0) rescale_o(f);
+            l *= f;
+            m_used = m_new;
           }
-          l *= f;
-          m_used = m_new;
-        }
-        const float neg = -m_used * c;
-        if (q == 0 && t == 0) LLB_TS(9, cnt - 1);
-        const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
-        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+          const float neg = -m_used * c;
+          const float2 neg2 = make_float2(neg, neg);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 tt = __ffma2_rn(
-                make_float2(__uint_as_float(sv[cc][2 * i]), __uint_as_float(sv[cc][2 * i + 1])), c2, neg2);
-            float2 pp;
-            if constexpr ((kDbg & 128) != 0) {
-              pk[i] = sv[cc][2 * i];
-              continue;
-            }
-            if constexpr ((kDbg & 8) != 0) {
-              pp = tt;
-            } else if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
-              pp = exp2_poly2(tt);
-            } else {
-              pp.x = ex2_approx(tt.x);
-              pp.y = ex2_approx(tt.y);
-            }
-            if (i & 1) lb = __fadd2_rn(lb, pp);
-            else la = __fadd2_rn(la, pp);
-            pk[i] = pack_bf16x2(pp.x, pp.y);
-          }
-          if constexpr (kPTmem) {
-            if constexpr ((kDbg & 64) != 0) {
-              if (pk[3] == 0x12345678u) l += 1.0f;  // keeps pk alive without the TMEM store
-            } else {
-              tmem_st16(t_s + cc * 16, pk);
-            }
+          for (int cc = 0; cc < 4; ++cc) {
+            exp_chunk(sv[cc], cc, c2, neg2, la, lb);
             if (cc == 1 && p.split_p) {
               // keys 0..63 of P_t(j) are complete: the MMA warp can start PV on them now
               tmem_wait_st();
@@ -1238,43 +630,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               __syncwarp();
               if (lane == 0) mbar_arrive(phalf_bar(t));
             }
-          } else {
-            // the P buffer is still being read by PV_t(j-1) until its commit arrives
-            if (!prev_pv_done) {
-              mbar_wait(odone_bar(t), (cnt - 2) & 1);
-              prev_pv_done = true;
-            }
-            // P tile [128 rows x 128 keys], K-major SW128: two 64-key boxes, 16-byte chunks XOR row%8
-            uint8_t* prow = p_gen + t * kTileBytes + (cc >> 1) * kBoxBytes + row_in_tile * 128;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int ch = (cc & 1) * 4 + i;
-              *reinterpret_cast<uint4*>(prow + ((ch ^ (row_in_tile & 7)) << 4)) =
-                  make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-            }
           }
         }
         la = __fadd2_rn(la, lb);
         l += la.x + la.y;
-        if (q == 0 && t == 0) LLB_TS(10, cnt - 1);
-        if constexpr (kPTmem) {
-          tmem_wait_st();
-          if (q == 0 && t == 0) LLB_TS(11, cnt - 1);
-        } else {
-          fence_proxy_async_smem();
-        }
+        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (q == 0) LLB_TS(t == 0 ? 1 : 7, cnt - 1);
         if (lane == 0) mbar_arrive(pfull_bar(t));
       }
       // ---- segment epilogue
-      if constexpr ((kDbg & 512) != 0) {
-        mbar_wait(odone_bar(t), segcnt & 1);
-        segcnt++;
-      } else {
-        mbar_wait(odone_bar(t), (cnt - 1) & 1);
-      }
+      mbar_wait(odone_bar(t), (cnt - 1) & 1);
       tc_fence_after();
       const bool tail_part = sg.in_remainder() && sg.t0 > 0;     // earlier kv tiles live in CTA blockIdx.x - 1
       const bool head_part = sg.in_remainder() && sg.t1 < sg.T;  // later kv tiles live in CTA blockIdx.x + 1
@@ -1367,7 +733,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(ofree_bar(t));
     }
-    }  // !kWide
   }
 
   tc_fence_before();
@@ -1378,17 +743,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <bool kPTmem, int kPoly, bool kHalf = false, bool kWide = false>
+template <bool kOpt>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
-  using Cfg = AttnCfg<kPTmem, kWide>;
-  LLB_SET_MAX_SMEM((attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>), Cfg::kSmemBytes);
+  LLB_SET_MAX_SMEM((attn_fwd_kernel<kOpt>), kAttnSmemBytes);
   // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
   // partial-merge flag wait relies on
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = kAttnSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   unsigned n_attr = 0;
@@ -1408,18 +772,12 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPTmem, kPoly, kHalf, kWide>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kOpt>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
 
 }  // namespace llb
-
-#if (LLB_ATTN_DBG & 2048)
-extern "C" int llb_attn_debug_ts(long long* host_buf) {  // [12][kTsSteps], instrumented builds only
-  return cudaMemcpyFromSymbol(host_buf, llb::g_attn_ts, sizeof(llb::g_attn_ts)) == cudaSuccess ? llb::kTsSteps : -1;
-}
-#endif
 
 extern "C" int64_t llb_attn_workspace_bytes(void) {
   const int sms = llb::device_sm_count();
@@ -1474,37 +832,13 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     p.shard = *shard;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // variant bit 0: P through shared memory instead of TMEM; bit 1: MUFU-only exp2 (no polynomial);
-  // bit 2: hand P to the MMA warp in two 64-key halves (TMEM-P path; measured 1.5 % slower on the
-  // steady-state shape, 5 % faster on the 18720 x 18720 recache shape - off by default)
-  // bit 3: half-tile pipeline (TMEM-P path): two 64-key halves per key tile with their own S buffers and barriers
+  // variant bit 2 (4): hand P to the MMA warp in two 64-key halves (measured 1.5 % slower on the steady-state
+  // shape, 5 % faster on the 18720 x 18720 recache shape - off by default);
+  // variant bit 5 (32): optimistic-exponent softmax loop (kOpt above; excludes the split hand-over)
+  if (variant & 32) {
+    p.split_p = 0;
+    return launch_attn<true>(tq, tk, tv, p, grid, s);
+  }
   p.split_p = (variant & 4) ? 1 : 0;
-  // bit 4: two softmax warpgroups per Q tile (640 threads, half a row per thread)
-  if ((variant & 16) && !(variant & 1)) {
-    p.split_p = 0;
-    return (variant & 2) ? launch_attn<true, 0, false, true>(tq, tk, tv, p, grid, s)
-                         : launch_attn<true, 4, false, true>(tq, tk, tv, p, grid, s);
-  }
-  if ((variant & 8) && !(variant & 1)) {
-    p.split_p = 0;
-    return (variant & 2) ? launch_attn<true, 0, true>(tq, tk, tv, p, grid, s)
-                         : launch_attn<true, 4, true>(tq, tk, tv, p, grid, s);
-  }
-#ifdef LLB_ATTN_POLY_SWEEP
-  // experiment builds only: LLB_ATTN_POLY = n sends every n-th probability pair through the polynomial (1 = all of them)
-  if (const char* e = getenv("LLB_ATTN_POLY")) {
-    switch (atoi(e)) {
-      case 1: return launch_attn<true, 1>(tq, tk, tv, p, grid, s);
-      case 2: return launch_attn<true, 2>(tq, tk, tv, p, grid, s);
-      case 3: return launch_attn<true, 3>(tq, tk, tv, p, grid, s);
-      default: break;
-    }
-  }
-#endif
-  switch (variant & 3) {
-    case 1: return launch_attn<false, 4>(tq, tk, tv, p, grid, s);
-    case 2: return launch_attn<true, 0>(tq, tk, tv, p, grid, s);
-    case 3: return launch_attn<false, 0>(tq, tk, tv, p, grid, s);
-    default: return launch_attn<true, 4>(tq, tk, tv, p, grid, s);
-  }
+  return launch_attn<false>(tq, tk, tv, p, grid, s);
 }

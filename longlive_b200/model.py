@@ -28,6 +28,7 @@ What the reference does per block and what runs here instead:
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -136,7 +137,7 @@ class CausalWanModel(nn.Module):
         self.gradient_checkpointing = False
 
         self.use_cuda_graph = True
-        self.attn_variant = 0
+        self.attn_variant = int(os.environ.get("LLB_ATTN_VARIANT", "0"))  # llb_attn_fwd variant bits (A/B runs)
         # optional W8A8 (e4m3) linears inside the blocks (q/k/v, o, cross q/o, ffn); set before the
         # first forward or call refresh_weights() afterwards
         self.fp8_linears = False

@@ -59,7 +59,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 8, 10, 16, 18], ids=["v0", "v1", "v2", "v3", "v4_split_p", "v8_half", "v10_half_mufu", "v16_wide", "v18_wide_mufu"])
+@pytest.mark.parametrize("variant", [0, 4, 32], ids=["v0", "v4_split_p", "v32_optimistic"])
 @pytest.mark.parametrize("Lq,H,rows,segs", ATTN_CASES)
 def test_attention(Lq, H, rows, segs, variant):
     ops = _ops()
@@ -80,7 +80,7 @@ def test_attention(Lq, H, rows, segs, variant):
     assert torch.equal(out, out2), "second launch on the same workspace differs"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 8, 10, 16, 18], ids=["v0", "v1", "v2", "v3", "v4_split_p", "v8_half", "v10_half_mufu", "v16_wide", "v18_wide_mufu"])
+@pytest.mark.parametrize("variant", [0, 4, 32], ids=["v0", "v4_split_p", "v32_optimistic"])
 def test_attention_large_logits(variant):
     """Row maxima that grow tile after tile exercise the lazy O-rescale path."""
     ops = _ops()

@@ -126,9 +126,11 @@ def _check_240(res, switched):
     print({k: v for k, v in res.items() if k not in ("rel_l2_per_chunk", "profile")})
     assert len(errs) == 80
     assert max(errs) <= 1e-2, (max(errs), errs)                      # north star: rel-L2 <= 1e-2 per chunk
-    # no drift growth over 240 frames: last ten chunks at the level of the first ten, flat trend
+    # no drift GROWTH over 240 frames: last ten chunks not above the level of the first ten, no upward trend
+    # (with prompt switches the level steps with the prompt - 7.7e-3 down to 6.2e-3 for the longer prompts -
+    # so the fitted slope may be negative; measured: +6e-8 per chunk single prompt, -2.2e-5 with switches)
     assert res["mean_last_10"] <= 1.15 * res["mean_first_10"] + 3e-4, res
-    assert abs(res["slope_per_chunk"]) <= 5e-6, res["slope_per_chunk"]
+    assert res["slope_per_chunk"] <= 5e-6, res["slope_per_chunk"]
     # integer contract at the end of the run
     assert res["global_end"] == res["oracle_global_end"] == 240 * 1560 == 374400
     assert res["local_end"] == res["oracle_local_end"] == 12 * 1560 == 18720

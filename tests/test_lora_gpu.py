@@ -12,7 +12,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-GATE = 8e-3   # flow prediction rel-L2, merged CUDA path vs unmerged bf16 oracle (lands at ~3e-3)
+GATE = 9e-3   # flow prediction rel-L2, merged CUDA path vs unmerged bf16 oracle: lands at 7.1e-3 on B200 (the
+              # unmerged path rounds x A, B (x A), the scaling and the sum to bf16 one by one; the LoRA delta is half of W)
 
 
 def rel_l2(a, b):
