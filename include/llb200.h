@@ -111,9 +111,11 @@ typedef struct llb_step_params {
 #define LLB_MAX_RANKS 8
 typedef struct llb_qkv_shard {
   int32_t n_ranks;
-  int32_t heads_per_rank;
+  int32_t heads_per_rank;       /* width of every rank's buffers in heads (the most heads any rank owns) */
   int32_t row0;                 /* global token row of local row 0                           */
-  int32_t reserved;
+  int32_t round_robin;          /* 0: head h -> rank h / heads_per_rank (needs n_heads % n_ranks == 0);
+                                 * 1: head h -> rank h % n_ranks, local head h / n_ranks (any n_ranks <= n_heads,
+                                 *    e.g. 12 heads over 8 ranks: ranks 0-3 own two heads, ranks 4-7 one)   */
   void* q_peers[LLB_MAX_RANKS]; /* rank r: Q buffer [L_total, heads_per_rank*128]              */
   void* k_peers[LLB_MAX_RANKS]; /* rank r: K ring   [cache_rows, heads_per_rank*128]           */
   void* v_peers[LLB_MAX_RANKS];
@@ -123,7 +125,8 @@ typedef struct llb_out_shard {
   int32_t n_ranks;
   int32_t rows_per_rank;          /* token rows owned by each rank                             */
   int32_t head_col0;              /* first output column of this rank's heads (head0 * 128)    */
-  int32_t reserved;
+  int32_t head_col_stride;        /* columns between consecutive local heads; 0 = 128 (contiguous heads),
+                                   * n_ranks * 128 for the round-robin head map                  */
   int64_t ld_out;                 /* leading dimension of the peers' output buffers            */
   void* out_peers[LLB_MAX_RANKS]; /* rank r: attention output [rows_per_rank, ld_out]          */
 } llb_out_shard;

@@ -85,7 +85,7 @@ class QkvShard(C.Structure):
     """llb_qkv_shard: head-parallel destination table of llb_rmsnorm_rope_append."""
 
     _fields_ = [("n_ranks", C.c_int32), ("heads_per_rank", C.c_int32), ("row0", C.c_int32),
-                ("reserved", C.c_int32), ("q_peers", C.c_void_p * LLB_MAX_RANKS),
+                ("round_robin", C.c_int32), ("q_peers", C.c_void_p * LLB_MAX_RANKS),
                 ("k_peers", C.c_void_p * LLB_MAX_RANKS), ("v_peers", C.c_void_p * LLB_MAX_RANKS)]
 
 
@@ -93,7 +93,7 @@ class OutShard(C.Structure):
     """llb_out_shard: head-parallel destination table of llb_attn_fwd."""
 
     _fields_ = [("n_ranks", C.c_int32), ("rows_per_rank", C.c_int32), ("head_col0", C.c_int32),
-                ("reserved", C.c_int32), ("ld_out", C.c_int64), ("out_peers", C.c_void_p * LLB_MAX_RANKS)]
+                ("head_col_stride", C.c_int32), ("ld_out", C.c_int64), ("out_peers", C.c_void_p * LLB_MAX_RANKS)]
 
 class Conv3dDesc(C.Structure):
     """llb_conv3d_desc (include/llb200.h): one causal convolution over channels-last frame rings."""

@@ -44,6 +44,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 
 namespace llb {
 
@@ -52,7 +54,6 @@ constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile 
 constexpr int kBoxBytes = 128 * 64 * 2;
 constexpr int kMinSplitTiles = 16;  // stream-K only when an item has at least this many kv tiles
 constexpr int kStages = 5;          // K/V tiles in flight
-constexpr int kPoly = 4;            // every 4th probability pair goes through the FMA-pipe polynomial exp2
 constexpr int kAttnSmemBytes = 1024 + 2 * kTileBytes + kStages * kTileBytes + 256;
 
 // workspace per CTA: partial O [2 tiles][32 col4][128 rows] float4, (m,l) [2][128] float2, flags [2][128]
@@ -70,7 +71,6 @@ struct AttnParams {
   float scale_log2;
   const llb_step_params* segs;
   uint8_t* workspace;  // gridDim.x * kWsPerCta bytes, flags zero-initialised once
-  int split_p;          // TMEM-P path: hand P to the MMA warp in two 64-key halves
   llb_out_shard shard; // n_ranks == 1: single GPU
 };
 
@@ -230,12 +230,11 @@ struct SegIter {
   }
 };
 
-// kOpt ("optimistic exponent"): with lazy rescaling the exponent offset of tile j is, in the common case, the
-// running maximum left by tile j-1, so the exponentials do not have to wait for tile j's own row maximum.  The
-// kOpt softmax loop exponentiates S_t(j) against the OLD maximum while it scans for the new one in the same pass
-// and only redoes the tile (after rescaling O) in the rare case that the maximum grew by more than 2^8; the
-// ~300-cycle max phase leaves the QK -> softmax -> PV chain that bounds this kernel.
-template <bool kOpt>
+// kPoly: every kPoly-th pair of probabilities is exponentiated on the FMA pipe (exp2_poly2) instead of MUFU
+// (0 = MUFU only).  ncu (profiles/r02_attn_ncu_source.md): the softmax warps are ISSUE bound - one warp per
+// scheduler, 40 % of its cycles issuing and 37 % in fixed-latency waits, XU (MUFU) pipe 44 % busy - so the
+// polynomial (12 instructions per pair against 2) is only worth what MUFU time it removes from the chain.
+template <int kPoly>
 __global__ void __maxnreg__(168)  // = 65536 / 384 threads, rounded down to the allocation unit
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -255,7 +254,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto ofree_bar = [&](int s) { return bar_base + 8u * (10 + s); };
   auto kvfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
   auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
-  auto phalf_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };  // first half of P_t(j) is in TMEM
   const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
@@ -274,7 +272,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
       mbar_init(ofree_bar(s), 4);
-      mbar_init(phalf_bar(s), 4);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
@@ -366,9 +363,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                   idesc_qk, kk != 0);
         }
       };
-      auto issue_pv = [&](int t, uint32_t vst, bool first, int kk0, int kk1) {
+      auto issue_pv = [&](int t, uint32_t vst, bool first) {
 #pragma unroll
-        for (int kk = kk0; kk < kk1; ++kk) {
+        for (int kk = 0; kk < 8; ++kk) {
           // V tile: rows = keys (K dim), two 64-wide d boxes 16 KB apart (MN dim); 16 keys per MMA;
           // A = P_t (bf16, 8 TMEM columns per 16 keys)
           const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
@@ -436,19 +433,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             advance();
           }
           // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
-          // (split: the first 64 keys of P_0(j) arrive while the softmax warps still exponentiate the rest)
-          if (p.split_p) {
-            mbar_wait(phalf_bar(0), pcnt0 & 1);
-            tc_fence_after();
-            if (elect_one()) issue_pv(0, vst, j == 0, 0, 4);
-            __syncwarp();
-          }
           mbar_wait(pfull_bar(0), pcnt0 & 1);
           pcnt0++;
           tc_fence_after();
           if (elect_one()) {
-            if (p.split_p) issue_pv(0, vst, false, 4, 8);
-            else issue_pv(0, vst, j == 0, 0, 8);
+            issue_pv(0, vst, j == 0);
             umma_commit(odone_bar(0));
             if (more) {
               issue_qk(0, kst);
@@ -462,18 +451,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
           __syncwarp();
           if (has1) {
-            if (p.split_p) {
-              mbar_wait(phalf_bar(1), pcnt1 & 1);
-              tc_fence_after();
-              if (elect_one()) issue_pv(1, vst, j == 0, 0, 4);
-              __syncwarp();
-            }
             mbar_wait(pfull_bar(1), pcnt1 & 1);
             pcnt1++;
             tc_fence_after();
             if (elect_one()) {
-              if (p.split_p) issue_pv(1, vst, false, 4, 8);
-              else issue_pv(1, vst, j == 0, 0, 8);
+              issue_pv(1, vst, j == 0);
               umma_commit(odone_bar(1));
               umma_commit(kvempty_bar(vstage));
               if (more) {
@@ -510,7 +492,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int i = 0; i < 16; ++i) {
         const float2 tt = __ffma2_rn(make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, neg2);
         float2 pp;
-        if ((i % kPoly) == kPoly - 1) {
+        if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) {
           pp = exp2_poly2(tt);
         } else {
           pp.x = ex2_approx(tt.x);
@@ -551,55 +533,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(sfull_bar(t), cnt & 1);
         cnt++;
         tc_fence_after();
-        uint32_t sv[4][32];
+        // The tile body exists twice: full tiles (the common case) carry no masking code at all - as one body with
+        // a run-time `valid < 128` test ptxas if-converted the masking into 128 ISETP + 128 SEL executed on EVERY
+        // tile, 30 % of the softmax instructions (profiles/r02_attn_ncu_source.md)
+        auto tile = [&](auto masked_tag) {
+          constexpr bool kMasked = decltype(masked_tag)::value;
+          uint32_t sv[4][32];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
-        tmem_wait_ld();
-        if (valid < 128) {
+          for (int cc = 0; cc < 4; ++cc) tmem_ld32(t_s + cc * 32, sv[cc]);
+          tmem_wait_ld();
+          if constexpr (kMasked) {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
+            for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
-        }
-        const float2 c2 = make_float2(c, c);
-        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-        if (kOpt && j > sg.t0) {
-          // ---- optimistic pass: exponentiate against the maximum the previous tiles left while scanning for
-          // this tile's own maximum (one fused pass over the row)
-          const float neg_old = -m_used * c;
-          const float2 neg2 = make_float2(neg_old, neg_old);
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[cc][i]), __uint_as_float(sv[cc][i + 1])));
-              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[cc][i + 2]), __uint_as_float(sv[cc][i + 3])));
-              mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[cc][i + 4]), __uint_as_float(sv[cc][i + 5])));
-              mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[cc][i + 6]), __uint_as_float(sv[cc][i + 7])));
-            }
-            exp_chunk(sv[cc], cc, c2, neg2, la, lb);
+              for (int i = 0; i < 32; ++i)
+                if (cc * 32 + i >= valid) sv[cc][i] = 0xff800000u;  // -inf
           }
-          const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-          const bool need = (m_new - m_used) * c > 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            // rare: the maximum grew by more than 2^8.  S_t(j) ready implies PV_t(j-1) complete (issued before
-            // QK_t(j)), so O is stable: rescale it, then redo this tile against the new maximum (S is still in
-            // registers; the P columns written above are simply overwritten)
-            tmem_wait_st();
-            const float f = ex2_approx((m_used - m_new) * c);
-            rescale_o(f);
-            l *= f;
-            m_used = m_new;
-            const float neg_new = -m_used * c;
-            const float2 neg2n = make_float2(neg_new, neg_new);
-            la = make_float2(0.f, 0.f);
-            lb = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) exp_chunk(sv[cc], cc, c2, neg2n, la, lb);
-          }
-        } else {
           float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -613,27 +562,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const bool need = (m_new - m_used) * c > 8.0f;
           if (__any_sync(0xffffffffu, need)) {
             const float f = ex2_approx((m_used - m_new) * c);  // 0 on the first tile (m_used=-inf)
-            // O must be stable: PV_t(j-1) complete, which S_t(j) being ready implies
+            // O must be stable: PV_t(j-1) complete, which S_t(j) being ready implies (issued before QK_t(j))
             if (j > sg.t0) rescale_o(f);
             l *= f;
             m_used = m_new;
           }
           const float neg = -m_used * c;
-          const float2 neg2 = make_float2(neg, neg);
+          const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
+          float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            exp_chunk(sv[cc], cc, c2, neg2, la, lb);
-            if (cc == 1 && p.split_p) {
-              // keys 0..63 of P_t(j) are complete: the MMA warp can start PV on them now
-              tmem_wait_st();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(phalf_bar(t));
-            }
-          }
-        }
-        la = __fadd2_rn(la, lb);
-        l += la.x + la.y;
+          for (int cc = 0; cc < 4; ++cc) exp_chunk(sv[cc], cc, c2, neg2, la, lb);
+          la = __fadd2_rn(la, lb);
+          l += la.x + la.y;
+        };
+        if (valid < 128) tile(std::true_type{});
+        else tile(std::false_type{});
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -684,7 +627,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int r = grow / p.shard.rows_per_rank;
         orow = static_cast<__nv_bfloat16*>(p.shard.out_peers[r]) +
                static_cast<int64_t>(grow - r * p.shard.rows_per_rank) * p.shard.ld_out + p.shard.head_col0 +
-               head * 128;
+               head * p.shard.head_col_stride;
       }
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
@@ -743,10 +686,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <bool kOpt>
+template <int kPoly>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
-  LLB_SET_MAX_SMEM((attn_fwd_kernel<kOpt>), kAttnSmemBytes);
+  LLB_SET_MAX_SMEM((attn_fwd_kernel<kPoly>), kAttnSmemBytes);
   // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
   // partial-merge flag wait relies on
   cudaLaunchConfig_t cfg = {};
@@ -772,7 +715,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kOpt>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPoly>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -826,19 +769,19 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.shard.n_ranks = 1;
   if (shard != nullptr && shard->n_ranks > 1) {
     LLB_CHECK_ARG(shard->n_ranks <= LLB_MAX_RANKS && shard->rows_per_rank > 0 && shard->ld_out % 8 == 0 &&
-                      shard->head_col0 % 8 == 0, "attn: bad output shard description");
+                      shard->head_col0 % 8 == 0 && shard->head_col_stride % 8 == 0 && shard->head_col_stride >= 0,
+                  "attn: bad output shard description");
     for (int r = 0; r < shard->n_ranks; ++r)
       LLB_CHECK_ARG(shard->out_peers[r] != nullptr, "attn: null peer pointer");
     p.shard = *shard;
   }
+  if (p.shard.head_col_stride == 0) p.shard.head_col_stride = 128;  // contiguous local heads
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // variant bit 2 (4): hand P to the MMA warp in two 64-key halves (measured 1.5 % slower on the steady-state
-  // shape, 5 % faster on the 18720 x 18720 recache shape - off by default);
-  // variant bit 5 (32): optimistic-exponent softmax loop (kOpt above; excludes the split hand-over)
-  if (variant & 32) {
-    p.split_p = 0;
-    return launch_attn<true>(tq, tk, tv, p, grid, s);
+  // variant: polynomial-exp2 period of the softmax loop (experiment knob; every build ships all three):
+  //   0 -> every 4th probability pair on the FMA pipe (default), 1 -> MUFU only, 2 -> every 8th pair
+  switch (variant & 3) {
+    case 1: return launch_attn<0>(tq, tk, tv, p, grid, s);
+    case 2: return launch_attn<8>(tq, tk, tv, p, grid, s);
+    default: return launch_attn<4>(tq, tk, tv, p, grid, s);
   }
-  p.split_p = (variant & 4) ? 1 : 0;
-  return launch_attn<false>(tq, tk, tv, p, grid, s);
 }

@@ -304,6 +304,19 @@ __device__ __forceinline__ int ring_dst_row(const llb_step_params* sp, int row) 
   return -1;
 }
 
+// Head-parallel destination of the 16-byte vector vi of a [*, C] row (head = vi / 16): owner rank and vector
+// index inside that rank's [*, heads_per_rank * 128] buffer.
+__device__ __forceinline__ void shard_slot(const llb_qkv_shard& sh, int vi, int vec_per_rank, int& r, int& lv) {
+  if (sh.round_robin) {
+    const int head = vi >> 4;
+    r = head % sh.n_ranks;
+    lv = (head / sh.n_ranks) * 16 + (vi & 15);
+  } else {
+    r = vi / vec_per_rank;
+    lv = vi - r * vec_per_rank;
+  }
+}
+
 // One warp per (token row, part) with part = blockIdx.y: 0 = q, 1 = k, 2 = v.  Splitting the row three ways
 // keeps the per-thread state at one 3 KB vector set (70 registers, three CTAs per SM) instead of five, which
 // is what this latency-bound pass needs: more rows in flight, not more loads per thread.
@@ -342,7 +355,8 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
         if (!sharded) {
           vo[vi] = v;
         } else {
-          const int r = vi / vec_per_rank, lv = vi - r * vec_per_rank;
+          int r, lv;
+          shard_slot(sh, vi, vec_per_rank, r, lv);
           reinterpret_cast<uint4*>(sh.v_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = v;
         }
       }
@@ -392,8 +406,10 @@ rmsnorm_rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld_qkv
         orow[vi] = ov;
       } else {
         // head exchange fused into the store: this 16-byte vector belongs to head vi/16, owned by
-        // rank (vi/16)/heads_per_rank; write it straight into that rank's (peer-mapped) buffers
-        const int r = vi / vec_per_rank, lv = vi - r * vec_per_rank;
+        // rank (vi/16)/heads_per_rank (or (vi/16) % n_ranks with the round-robin map); write it straight into
+        // that rank's (peer-mapped) buffers
+        int r, lv;
+        shard_slot(sh, vi, vec_per_rank, r, lv);
         if (part == 0) reinterpret_cast<uint4*>(sh.q_peers[r])[static_cast<int64_t>(grow) * ldp + lv] = ov;
         else reinterpret_cast<uint4*>(sh.k_peers[r])[static_cast<int64_t>(dst) * ldp + lv] = ov;
       }
@@ -599,7 +615,9 @@ extern "C" int llb_rmsnorm_rope_append(const void* qkv, int64_t ld_qkv, void* q_
   sh.heads_per_rank = n_heads;
   if (shard != nullptr) {
     sh = *shard;
-    LLB_CHECK_ARG(sh.n_ranks >= 1 && sh.n_ranks <= LLB_MAX_RANKS && sh.heads_per_rank * sh.n_ranks == n_heads,
+    LLB_CHECK_ARG(sh.n_ranks >= 1 && sh.n_ranks <= LLB_MAX_RANKS &&
+                      (sh.round_robin ? (sh.n_ranks <= n_heads && sh.heads_per_rank == (n_heads + sh.n_ranks - 1) / sh.n_ranks)
+                                      : sh.heads_per_rank * sh.n_ranks == n_heads),
                   "rmsnorm_rope_append: bad shard description");
     for (int r = 0; r < sh.n_ranks && sh.n_ranks > 1; ++r)
       LLB_CHECK_ARG(sh.q_peers[r] && sh.k_peers[r] && sh.v_peers[r], "rmsnorm_rope_append: null peer pointer");

@@ -218,7 +218,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, segs_dev: torch
     _req(q, "q"); _req(k, "k"); _req(v, "v")
     assert segs_dev.dtype == torch.int32 and segs_dev.numel() >= STEP_PARAMS_INT32 and segs_dev.is_cuda
     Lq = q.shape[0]
-    assert q.shape[1] == n_heads * 128 and k.shape[1] == n_heads * 128 and v.shape == k.shape
+    # (head-parallel buffers may be wider than the heads this launch covers: only the first n_heads * 128 columns are read)
+    assert q.shape[1] >= n_heads * 128 and k.shape[1] >= n_heads * 128 and v.shape == k.shape
     if out is None:
         out = torch.empty((Lq, n_heads * 128), dtype=torch.bfloat16, device=q.device)
     if scale is None:

@@ -15,7 +15,9 @@ each followed by llb_peer_barrier (a one-CTA flag exchange over the same mapping
 [L, 64] head output.  Cross-attention needs no exchange (text K/V are replicated).
 
 Every rank runs the same pipeline code on the same inputs (same seeds), so host-side ring plans
-are identical; P must divide the head count and the tokens per chunk (P in {2, 4} for Wan-1.3B).
+are identical; P must divide the tokens per chunk.  P in {2, 3, 4, 6} divides the 12 heads of Wan-1.3B
+(contiguous head blocks); P = 8 deals the heads round-robin (ranks 0-3 own two heads, ranks 4-7 one: the
+attention step then scales like P = 6 while every GEMM / row kernel scales by 8).
 """
 from __future__ import annotations
 
@@ -68,8 +70,13 @@ class UlyssesCausalWanModel(CausalWanModel):
                        use_cuda_graph: bool = False):
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.P = dist.get_rank(self.group), dist.get_world_size(self.group)
-        assert self.num_heads % self.P == 0 and self.P <= _lib.LLB_MAX_RANKS
-        self.hp = self.num_heads // self.P
+        assert self.P <= min(_lib.LLB_MAX_RANKS, self.num_heads)
+        # P divides the head count: contiguous head blocks.  Otherwise (12 heads over 8 ranks) heads are dealt
+        # round-robin: rank r owns heads r, r + P, ... - ranks 0-3 two heads, ranks 4-7 one; every rank's
+        # buffers are `hp` = 2 heads wide and the attention launch of a rank covers the heads it owns.
+        self.round_robin = self.num_heads % self.P != 0
+        self.hp = -(-self.num_heads // self.P)
+        self.my_heads = len(range(self.rank, self.num_heads, self.P)) if self.round_robin else self.hp
         dev = self.patch_embedding.weight.device
         hw = self.hp * 128
         kv_bytes = self.num_layers * 2 * cache_tokens * hw * 2
@@ -105,6 +112,33 @@ class UlyssesCausalWanModel(CausalWanModel):
     def _barrier(self):
         ops.peer_barrier(self.flag_ptrs_dev, self.rank, self.P, self.epoch)
 
+    # ---- optional per-phase timeline (eager mode only): CUDA events around the five phases of every block
+    PHASES = ("dense", "append_send", "barrier_qkv", "attn_send", "barrier_out")
+
+    def start_timeline(self):
+        """Record events for the next forwards (use_cuda_graph must be False); read with phase_ms()."""
+        assert not self.use_cuda_graph, "the timeline records events between launches: eager mode only"
+        self._tl = []
+
+    def _mark(self, phase: str):
+        tl = getattr(self, "_tl", None)
+        if tl is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            tl.append((phase, ev))
+
+    def phase_ms(self) -> dict:
+        """Milliseconds per phase summed over everything recorded since start_timeline(): each mark closes the
+        phase named by the PREVIOUS mark.  'barrier_*' = wait for the slowest rank + latency of the remote stores
+        that are still in flight; '*_send' = the producing kernel including its NVLink stores."""
+        torch.cuda.synchronize()
+        tl, self._tl = self._tl, None
+        out = {k: 0.0 for k in self.PHASES}
+        for (ph, a), (_, b) in zip(tl[:-1], tl[1:]):
+            if ph != "end":
+                out[ph] += a.elapsed_time(b)
+        return out
+
     def _run_blocks(self, b: dict, kv_cache, crossattn_cache, B: int, F: int, H: int, W: int):
         assert B == 1, "head-parallel mode handles one stream"
         Pk = self._packed
@@ -137,45 +171,69 @@ class UlyssesCausalWanModel(CausalWanModel):
         attn_local = self.attn_sym.local[:Lp]
         q_full = self.q_sym.local[:L]
         out_sh = _lib.OutShard()
-        out_sh.n_ranks, out_sh.rows_per_rank, out_sh.head_col0, out_sh.ld_out = P, Lp, r * hw, C_
+        out_sh.n_ranks, out_sh.rows_per_rank, out_sh.ld_out = P, Lp, C_
+        if self.round_robin:   # local head i is global head r + i * P
+            out_sh.head_col0, out_sh.head_col_stride = r * 128, P * 128
+        else:
+            out_sh.head_col0, out_sh.head_col_stride = r * hw, 128
         for j in range(P):
             out_sh.out_peers[j] = self.attn_sym.peer_ptrs[j]
+        f8 = self.fp8_linears
+
+        def lin(name, lw, a, **kw):
+            """One block Linear on this rank's token rows: bf16 GEMM, or W8A8 (a = (a8, scale)) when fp8_linears."""
+            if f8:
+                return ops.gemm_fp8(a[0], a[1], lw[name + "_w8"], lw[name + "_ws"], lw[name + "_b"], **kw)
+            return ops.gemm(a, lw[name + "_w"], lw[name + "_b"], **kw)
+
+        def ln_in(**kw):
+            if f8:
+                return ops.ln_modulate_fp8(x, b["a8"][rows], b["sa"][rows], eps=eps, **kw)
+            return ops.ln_modulate(x, eps=eps, out=xm, **kw)
+
+        def act_in(t, buf="a8"):
+            return ops.quant_rows_fp8(t, b[buf][rows], b["sa"][rows]) if f8 else t
+
+        self._mark("dense")
         for i, lw in enumerate(Pk["layers"]):
             m = b["mod"][i]
             e = [m[:, k * C_:(k + 1) * C_] for k in range(6)]
-            ops.ln_modulate(x, shift=e[0], scale=e[1], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
-            ops.gemm(xm, lw["qkv_w"], lw["qkv_b"], out=qkv)
+            lin("qkv", lw, ln_in(shift=e[0], scale=e[1], rows_per_frame=fs, row0=r0), out=qkv)
+            self._mark("append_send")
             sh = _lib.QkvShard()
-            sh.n_ranks, sh.heads_per_rank, sh.row0 = P, self.hp, r0
+            sh.n_ranks, sh.heads_per_rank, sh.row0, sh.round_robin = P, self.hp, r0, int(self.round_robin)
             for j in range(P):
                 sh.q_peers[j] = self.q_sym.peer_ptrs[j]
                 sh.k_peers[j] = self.k_sym[i].peer_ptrs[j]
                 sh.v_peers[j] = self.v_sym[i].peer_ptrs[j]
             ops.rmsnorm_rope_append(qkv, None, None, None, lw["nq"], lw["nk"], Pk["rope"], (gh, gw), b["params"],
                                     n_heads=self.num_heads, eps=eps, shard=sh)
+            self._mark("barrier_qkv")
             self._barrier()  # every rank's head slices (Q, K, V) have landed
+            self._mark("attn_send")
             k2 = kv_cache[i]["k"][0].view(-1, hw)
             v2 = kv_cache[i]["v"][0].view(-1, hw)
-            ops.attention(q_full, k2, v2, b["params"], n_heads=self.hp, out=q_full, variant=v, shard=out_sh)
+            ops.attention(q_full, k2, v2, b["params"], n_heads=self.my_heads, out=q_full, variant=v, shard=out_sh)
+            self._mark("barrier_out")
             self._barrier()  # every rank's token rows of the attention output have landed
-            ops.gemm(attn_local, lw["o_w"], lw["o_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2],
-                     rows_per_gate=fs, gate_row0=r0, res=x, out=x)
-            ops.ln_modulate(x, ln_w=lw["n3_w"], ln_b=lw["n3_b"], eps=eps, out=xm)
-            ops.gemm(xm, lw["cq_w"], lw["cq_b"], out=cq)
+            self._mark("dense")
+            lin("o", lw, act_in(attn_local), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[2], rows_per_gate=fs,
+                gate_row0=r0, res=x, out=x)
+            lin("cq", lw, ln_in(ln_w=lw["n3_w"], ln_b=lw["n3_b"]), out=cq)
             ops.rmsnorm(cq, lw["cnq"], eps, out=qbuf)
             ck, cv = crossattn_cache[i]["k"], crossattn_cache[i]["v"]
             ops.attention(qbuf, ck[0].view(-1, C_), cv[0].view(-1, C_), Pk["cross_segs"], n_heads=self.num_heads,
                           out=b["attn"][rows], variant=v)
-            ops.gemm(b["attn"][rows], lw["co_w"], lw["co_b"], epilogue=ops.EPI_BIAS_RES, res=x, out=x)
-            ops.ln_modulate(x, shift=e[3], scale=e[4], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
-            ops.gemm(xm, lw["f1_w"], lw["f1_b"], epilogue=ops.EPI_BIAS_GELU, out=h)
-            ops.gemm(h, lw["f2_w"], lw["f2_b"], epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
-                     gate_row0=r0, res=x, out=x)
+            lin("co", lw, act_in(b["attn"][rows]), epilogue=ops.EPI_BIAS_RES, res=x, out=x)
+            lin("f1", lw, ln_in(shift=e[3], scale=e[4], rows_per_frame=fs, row0=r0), epilogue=ops.EPI_BIAS_GELU, out=h)
+            lin("f2", lw, act_in(h, "h8"), epilogue=ops.EPI_BIAS_GATE_RES, gate=e[5], rows_per_gate=fs,
+                gate_row0=r0, res=x, out=x)
         b["e2"][:, :C_].copy_(b["e"]); b["e2"][:, C_:].copy_(b["e"])
         ops.modulation_table(Pk["head_mod"], b["e2"], out=b["hmod"])
         hm = b["hmod"][0]
         ops.ln_modulate(x, shift=hm[:, :C_], scale=hm[:, C_:], rows_per_frame=fs, row0=r0, eps=eps, out=xm)
         ops.gemm(xm, Pk["head_w"], Pk["head_b"], out=b["y"][r0:r0 + Lp])
+        self._mark("end")
         # gather the [L, 64] head output (tiny) so every rank can unpatchify the full chunk
         dist.all_gather_into_tensor(b["y"][:L], b["y"][r0:r0 + Lp].clone(), group=self.group)
         ops.unpatchify(b["y"][:L], self.out_dim, F, H, W, out=b["out"][0])

@@ -14,13 +14,17 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("P", [2, 4, 8])
 def test_sharded_append_and_attention_match_unsharded(P):
+    """P = 2, 4: contiguous head blocks; P = 8: 12 heads dealt round-robin (ranks 0-3 own two heads, 4-7 one)."""
     from longlive_b200 import _lib, ops
     H, F, gh, gw = 12, 3, 30, 52
     L, Cc, size = F * gh * gw, H * 128, 12 * 1560
-    hp, Lp = H // P, L // P
+    rr = H % P != 0
+    hp, Lp = -(-H // P), L // P
     hw = hp * 128
+    heads_of = [list(range(r, H, P)) if rr else list(range(r * hp, (r + 1) * hp)) for r in range(P)]
+    cols_of = [torch.cat([torch.arange(h * 128, (h + 1) * 128) for h in hs]).to(DEV) for hs in heads_of]
     g = torch.Generator(device="cpu").manual_seed(9)
     qkv = (torch.randn(L, 3 * Cc, generator=g)).to(torch.bfloat16).to(DEV)
     wq = (1 + 0.1 * torch.randn(Cc, generator=g)).to(torch.bfloat16).to(DEV)
@@ -40,26 +44,33 @@ def test_sharded_append_and_attention_match_unsharded(P):
 
     # ---- P emulated ranks: head-sharded Q / K / V, token-sharded attention output
     q_sh = [torch.zeros(L, hw, dtype=torch.bfloat16, device=DEV) for _ in range(P)]
-    k_sh = [old_k[:, r * hw:(r + 1) * hw].contiguous() for r in range(P)]
-    v_sh = [old_v[:, r * hw:(r + 1) * hw].contiguous() for r in range(P)]
+    def shard_of(t, r):   # rank r's [rows, hp * 128] buffer holding its heads of t (unused columns zero)
+        buf = torch.zeros(t.shape[0], hw, dtype=t.dtype, device=DEV)
+        buf[:, :cols_of[r].numel()] = t[:, cols_of[r]]
+        return buf
+    k_sh = [shard_of(old_k, r) for r in range(P)]
+    v_sh = [shard_of(old_v, r) for r in range(P)]
     o_sh = [torch.zeros(Lp, Cc, dtype=torch.bfloat16, device=DEV) for _ in range(P)]
     for r in range(P):  # token shard r sends its head slices to every "rank"
         sh = _lib.QkvShard()
-        sh.n_ranks, sh.heads_per_rank, sh.row0 = P, hp, r * Lp
+        sh.n_ranks, sh.heads_per_rank, sh.row0, sh.round_robin = P, hp, r * Lp, int(rr)
         for j in range(P):
             sh.q_peers[j], sh.k_peers[j], sh.v_peers[j] = q_sh[j].data_ptr(), k_sh[j].data_ptr(), v_sh[j].data_ptr()
         ops.rmsnorm_rope_append(qkv[r * Lp:(r + 1) * Lp], None, None, None, wq, wk, table, (gh, gw), sp,
                                 n_heads=H, shard=sh)
     for r in range(P):
-        assert torch.equal(q_sh[r], q_ref[:, r * hw:(r + 1) * hw])
-        assert torch.equal(k_sh[r], kc[:, r * hw:(r + 1) * hw])
-        assert torch.equal(v_sh[r], vc[:, r * hw:(r + 1) * hw])
+        n = cols_of[r].numel()
+        assert torch.equal(q_sh[r][:, :n], q_ref[:, cols_of[r]])
+        assert torch.equal(k_sh[r][:, :n], kc[:, cols_of[r]])
+        assert torch.equal(v_sh[r][:, :n], vc[:, cols_of[r]])
+        assert q_sh[r][:, n:].abs().max().item() == 0 if n < hw else True
     for r in range(P):  # head shard r returns its output columns to the owners of the token rows
         osd = _lib.OutShard()
-        osd.n_ranks, osd.rows_per_rank, osd.head_col0, osd.ld_out = P, Lp, r * hw, Cc
+        osd.n_ranks, osd.rows_per_rank, osd.ld_out = P, Lp, Cc
+        osd.head_col0, osd.head_col_stride = (r * 128, P * 128) if rr else (r * hw, 128)
         for j in range(P):
             osd.out_peers[j] = o_sh[j].data_ptr()
-        ops.attention(q_sh[r], k_sh[r], v_sh[r], sp, n_heads=hp, shard=osd)
+        ops.attention(q_sh[r], k_sh[r], v_sh[r], sp, n_heads=len(heads_of[r]), shard=osd)
     o_par = torch.cat(o_sh, 0)
     err = rel_l2(o_par, o_ref)
     print(f"P={P}: sharded vs unsharded attention rel-L2 {err:.3e}")
