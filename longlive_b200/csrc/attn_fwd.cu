@@ -722,6 +722,8 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 
 }  // namespace llb
 
+#include "attn_pair.cuh"
+
 extern "C" int64_t llb_attn_workspace_bytes(void) {
   const int sms = llb::device_sm_count();
   return static_cast<int64_t>(sms > 0 ? sms : 148) * llb::kWsPerCta;
@@ -777,6 +779,14 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   }
   if (p.shard.head_col_stride == 0) p.shard.head_col_stride = 128;  // contiguous local heads
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // variant bit 6 (64): the CTA-pair kernel (attn_pair.cuh)
+  if (variant & 64) {
+    LLB_CHECK_ARG(sms >= 2, "attn: the CTA-pair kernel needs at least two SMs");
+    CUtensorMap tk64;
+    rc = make_tmap_2d_bf16(&tk64, k, kv_rows, static_cast<uint64_t>(n_heads) * 128, ldk, 64, 64);
+    if (rc) return rc;
+    return launch_attn_pair(tq, tk64, tv, p, sms, s);
+  }
   // variant: polynomial-exp2 period of the softmax loop (experiment knob; every build ships all three):
   //   0 -> every 4th probability pair on the FMA pipe (default), 1 -> MUFU only, 2 -> every 8th pair
   switch (variant & 3) {
