@@ -346,6 +346,42 @@ def full_pipeline_sample(torch, dev, pipe_args):
                     "encoder + denoising + whole-clip VAE decode, all on libllb200 (random-init weights)"}
 
 
+def ulysses_sample(rank, world, local, timeout_s=420):
+    """N > 1 only, informational: ONE stream split head-parallel over the N ranks (longlive_b200/ulysses.py), beside
+    the headline (N independent streams).  Every rank spawns tools/ulysses_check.py as a CHILD process with its own
+    rendezvous port, so a failure or a hang of the optional path can never take the headline number down with it;
+    rank 0 returns the child's summary: FPS of the single stream, speed-up and efficiency against one GPU running the
+    same 21-frame job, rel-L2 of the latents against the single-GPU CUDA path."""
+    out = os.path.join(ROOT, "gpurun_out", f"bench_ulysses_P{world}.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if rank == 0 and os.path.exists(out):
+        os.remove(out)
+    env = dict(os.environ)
+    env.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(local), "MASTER_ADDR": "127.0.0.1",
+                "MASTER_PORT": str(int(os.environ.get("MASTER_PORT", "29500")) + 23)})
+    for k in ("TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ulysses_check.py"), "--frames", str(T_FRAMES), "--graph", "1",
+           "--out", out]
+    try:
+        proc = subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=timeout_s, text=True)
+        err = None if proc.returncode == 0 else f"exit {proc.returncode}: {proc.stderr[-300:]}"
+    except subprocess.TimeoutExpired:
+        err = f"timed out after {timeout_s} s"
+    if rank != 0:
+        return None
+    if not os.path.exists(out):
+        return {"error": err or "no output"}
+    d = json.load(open(out))
+    return {"P": d["P"], "video_fps_one_stream": d["fps_parallel"], "video_fps_one_gpu": d["fps_single"],
+            "speedup_vs_one_gpu": d["speedup"], "efficiency": d["efficiency"], "head_map": d["head_map"],
+            "heads_per_rank": d["heads_per_rank"], "max_rel_l2_vs_single_gpu": max(d["rel_l2_per_chunk_vs_single_gpu"]),
+            "cuda_graph": d["cuda_graph"], "error": err,
+            "what": "one 21-frame stream head-parallel over the N GPUs (tokens sharded for GEMMs / row kernels, heads for "
+                    "attention and the KV ring; the two exchanges per block are peer stores fused into the producing kernels), "
+                    "wall clock of the second pipeline call, against the same job on one GPU"}
+
+
 def attention_roofline(torch, ops, dev, iters=60):
     """Dominant kernel: self-attention at the steady-state shape, timed live with CUDA events on the
     launching stream, rotating over 4 K/V sets (460 MB > L2) like consecutive layers do."""
@@ -472,8 +508,18 @@ def run_ours(args):
             pipe.inference(noise_dev, ["synthetic prompt"], profile=True)
         steady = pipe.last_profile
     roof = attention_roofline(torch, ops, dev) if rank == 0 else None
+    used_graph = bool(model.use_cuda_graph)
+    uly = None
     if world > 1:
         dist.barrier()
+        if not args.no_ulysses:
+            del pipe, gen, model           # the child processes need the memory bandwidth, not the memory; tidy anyway
+            torch.cuda.empty_cache()
+            try:
+                uly = ulysses_sample(rank, world, local)
+            except Exception as e:  # informational: never fails the headline
+                uly = {"error": str(e)[:300]}
+            dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -491,7 +537,6 @@ def run_ours(args):
         except Exception as e:  # informational: never fails the headline
             text = {"error": str(e)[:200]}
     full = None
-    used_graph = bool(model.use_cuda_graph)
     if world == 1:
         try:
             del pipe, gen, model
@@ -540,6 +585,7 @@ def run_ours(args):
         "text_encoder": text,
         "full_pipeline": full,
         "reference_gpu": ref_gpu,
+        "ulysses": uly,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -554,6 +600,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-ulysses", action="store_true", help="N > 1: skip the head-parallel single-stream sample")
     ap.add_argument("--fp8-linears", action="store_true",
                     help="optional W8A8 (e4m3) linears inside the blocks; not the headline configuration")
     args = ap.parse_args()

@@ -231,7 +231,7 @@ struct SegIter {
 };
 
 // kPoly: every kPoly-th pair of probabilities is exponentiated on the FMA pipe (exp2_poly2) instead of MUFU
-// (0 = MUFU only).  ncu (profiles/r02_attn_ncu_source.md): the softmax warps are ISSUE bound - one warp per
+// (0 = MUFU only; shipped: 4 - MUFU only and every 8th pair measured the same within noise, profiles/r02_attn_pair.md).  ncu (profiles/r02_attn_ncu_source.md): the softmax warps are ISSUE bound - one warp per
 // scheduler, 40 % of its cycles issuing and 37 % in fixed-latency waits, XU (MUFU) pipe 44 % busy - so the
 // polynomial (12 instructions per pair against 2) is only worth what MUFU time it removes from the chain.
 template <int kPoly>
@@ -787,11 +787,5 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     if (rc) return rc;
     return launch_attn_pair(tq, tk64, tv, p, sms, s);
   }
-  // variant: polynomial-exp2 period of the softmax loop (experiment knob; every build ships all three):
-  //   0 -> every 4th probability pair on the FMA pipe (default), 1 -> MUFU only, 2 -> every 8th pair
-  switch (variant & 3) {
-    case 1: return launch_attn<0>(tq, tk, tv, p, grid, s);
-    case 2: return launch_attn<8>(tq, tk, tv, p, grid, s);
-    default: return launch_attn<4>(tq, tk, tv, p, grid, s);
-  }
+  return launch_attn<4>(tq, tk, tv, p, grid, s);
 }

@@ -24,6 +24,13 @@
 //
 // Scheduling is the single-CTA kernel's (persistent whole-item rounds + split remainder merged through the
 // workspace), with the cluster as the worker.
+//
+// STATUS (round 2, measured on B200, profiles/r02_attn_pair.md): bit-for-bit the same error against fp32 as the
+// single-CTA kernel on every test shape (tests/test_attn_gpu.py, variant 64), but NOT faster yet - 1170-1200 TFLOP/s
+// against 1230-1240 at Lq 4680 x Lk 18720 - so it is selectable (variant bit 6) and not the default.  Its own ncu
+// profile shows the decomposition working as intended (the softmax warpgroups wait for S 4 % of the time instead
+// of 49 %) and what it costs: two softmax warps per scheduler issue at 30 % each instead of 41 % alone (MIO / XU
+// queue throttling appears), and the ordering protocol adds ~330 cycles per tile.
 #pragma once
 
 namespace llb {
@@ -34,6 +41,7 @@ constexpr int kPairBarBytes = 512;
 constexpr int kPairXchgBytes = 128 * 4 + 2 * 128 * 4 + 64;  // m_ref[128], l_x[2][128], dec[4]
 constexpr int kPairSmemBytes = 1024 + kTileBytes + kPairStages * kHalfTileBytes + kPairBarBytes + kPairXchgBytes;
 constexpr int kPairPoly = 4;
+constexpr int kQkAhead = 4;                 // QK(j + 4) is issued right behind PV(j): see the MMA warp
 
 __device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -179,12 +187,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tma_load_2d_pair(dst, &tmap_v, mapa_shared(kvfull_bar(stage), 0), col + static_cast<int>(rank) * 64, row0);
             end_stage();
           };
-          // consumption order of the MMA warp: K_0, K_1, then V_j, K_{j+2} for j = 0 ..
+          // consumption order of the MMA warp: K_0 .. K_3, then V_j, K_{j+4} for j = 0 ..
           const int nt = sg.t1 - sg.t0;
           kv_it.seek(sg.t0);
           KvTileIter k_it = kv_it;
           int row0, valid;
-          for (int i = 0; i < 2 && i < nt; ++i) {
+          for (int i = 0; i < kQkAhead && i < nt; ++i) {
             k_it.get(row0, valid);
             load_k(row0);
             k_it.next();
@@ -193,7 +201,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             kv_it.get(row0, valid);
             load_v(row0);
             kv_it.next();
-            if (j + 2 < nt) {
+            if (j + kQkAhead < nt) {
               k_it.get(row0, valid);
               load_k(row0);
               k_it.next();
@@ -254,8 +262,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           __syncwarp();
         };
-        qk_step(0);
-        if (nt > 1) qk_step(1);
+        // Issue order = the order in which things become ready.  When a softmax warpgroup finishes tile j and starts
+        // tile j+2, two MMA groups become issuable together: PV(j) (P_c(j) is complete) and QK(j+4) (S_c(j+2) has just
+        // been read into registers, so its buffer is free).  Hence QKs run kQkAhead = 4 tiles ahead of the PVs:
+        // QK(0..3) up front (QK(2), QK(3) wait for the first reads of S_A, S_B), then PV(j), QK(j+4).  With QK(j+2)
+        // queued behind PV(j-1) instead, S(j+2) only became ready half a period late (first ncu profile of this kernel).
+        for (int i = 0; i < kQkAhead && i < nt; ++i) qk_step(i);
         // O of the previous item must have been drained before this item's first PV overwrites it
         mbar_wait(ofree_bar, (oseg & 1) ^ 1);
         oseg++;
@@ -274,7 +286,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             umma_commit_pair(kvempty_bar(vstage), 3);
           }
           __syncwarp();
-          if (j + 2 < nt) qk_step(j + 2);
+          if (j + kQkAhead < nt) qk_step(j + kQkAhead);
         }
       }
     }
@@ -296,7 +308,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t n_mine = 0, n_other = 0;  // key tiles handled so far by this chain / the other chain (barrier phases)
     LLB_PAIR_INIT_WORK();
 
-    auto exp_chunk = [&](const uint32_t (&s)[32], int cc, float2 c2, float2 neg2, float2& la, float2& lb) {
+    // wait_p: parity to wait for on p_free[ch] before the FIRST store of a tile (-1 = nothing to wait for)
+    auto exp_chunk = [&](const uint32_t (&s)[32], int cc, float2 c2, float2 neg2, float2& la, float2& lb, int wait_p) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -311,6 +324,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (i & 1) lb = __fadd2_rn(lb, pp);
         else la = __fadd2_rn(la, pp);
         pk[i] = pack_bf16x2(pp.x, pp.y);
+      }
+      if (cc == 0 && wait_p >= 0) {
+        // P_c still feeds PV of this chain's previous tile until that MMA group completes; the first 32 keys of
+        // this tile are exponentiated before the wait, which hides it
+        mbar_wait(pfree_bar(ch), static_cast<uint32_t>(wait_p));
+        tc_fence_after();
       }
       tmem_st16(t_p + cc * 16, pk);
     };
@@ -397,13 +416,9 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           const float neg = -m_seen * c;
           const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
           float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-          // P_c still feeds PV of this chain's previous tile until that MMA group completes
-          if (n_mine > 0) {
-            mbar_wait(pfree_bar(ch), (n_mine - 1) & 1);
-            tc_fence_after();
-          }
+          const int wait_p = n_mine > 0 ? static_cast<int>((n_mine - 1) & 1) : -1;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) exp_chunk(sv[cc], cc, c2, neg2, la, lb);
+          for (int cc = 0; cc < 4; ++cc) exp_chunk(sv[cc], cc, c2, neg2, la, lb, wait_p);
           la = __fadd2_rn(la, lb);
           l += la.x + la.y;
         };

@@ -337,8 +337,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on an mbarrier that may live in the peer CTA (address from mapa_shared)
+// Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does: what the arrival
+// publishes here are tcgen05 (TMEM) accesses, ordered by tcgen05.wait + tcgen05.fence::before_thread_sync on this side
+// and fence::after_thread_sync on the waiter's.  The explicit `.release.cluster` form compiles to MEMBAR.ALL.GPU +
+// ERRBAR per arrival - a third of the CTA-pair attention kernel's softmax time in its first ncu profile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA tile load into THIS CTA's shared memory whose completion bytes are counted on a barrier
 // that may belong to the peer CTA of the pair (the leader's "full" barrier).

@@ -59,7 +59,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 64], ids=["v0_poly4", "v1_mufu_only", "v2_poly8", "v64_pair"])
+@pytest.mark.parametrize("variant", [0, 64], ids=["v0", "v64_cta_pair"])
 @pytest.mark.parametrize("Lq,H,rows,segs", ATTN_CASES)
 def test_attention(Lq, H, rows, segs, variant):
     ops = _ops()
@@ -80,7 +80,7 @@ def test_attention(Lq, H, rows, segs, variant):
     assert torch.equal(out, out2), "second launch on the same workspace differs"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 64], ids=["v0_poly4", "v1_mufu_only", "v2_poly8", "v64_pair"])
+@pytest.mark.parametrize("variant", [0, 64], ids=["v0", "v64_cta_pair"])
 def test_attention_large_logits(variant):
     """Row maxima that grow tile after tile exercise the lazy O-rescale path."""
     ops = _ops()
