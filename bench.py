@@ -359,7 +359,10 @@ def ulysses_sample(rank, world, local, timeout_s=420):
     env = dict(os.environ)
     env.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(local), "MASTER_ADDR": "127.0.0.1",
                 "MASTER_PORT": str(int(os.environ.get("MASTER_PORT", "29500")) + 23)})
-    for k in ("TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE"):
+    # the children rendezvous on their OWN TCP store (rank 0 of the children creates it): drop everything that makes
+    # c10d look for the launcher's agent store (TORCHELASTIC_USE_AGENT_STORE) or identifies the parent's run
+    for k in [k for k in env if k.startswith("TORCHELASTIC_")] + ["GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "LOCAL_WORLD_SIZE",
+                                                                   "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE"]:
         env.pop(k, None)
     cmd = [sys.executable, os.path.join(ROOT, "tools", "ulysses_check.py"), "--frames", str(T_FRAMES), "--graph", "1",
            "--out", out]
