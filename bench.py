@@ -346,7 +346,7 @@ def full_pipeline_sample(torch, dev, pipe_args):
                     "encoder + denoising + whole-clip VAE decode, all on libllb200 (random-init weights)"}
 
 
-def ulysses_sample(rank, world, local, timeout_s=420):
+def ulysses_sample(rank, world, local, timeout_s=300):
     """N > 1 only, informational: ONE stream split head-parallel over the N ranks (longlive_b200/ulysses.py), beside
     the headline (N independent streams).  Every rank spawns tools/ulysses_check.py as a CHILD process with its own
     rendezvous port, so a failure or a hang of the optional path can never take the headline number down with it;
@@ -369,8 +369,9 @@ def ulysses_sample(rank, world, local, timeout_s=420):
     try:
         proc = subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=timeout_s, text=True)
         err = None if proc.returncode == 0 else f"exit {proc.returncode}: {proc.stderr[-300:]}"
-    except subprocess.TimeoutExpired:
-        err = f"timed out after {timeout_s} s"
+    except subprocess.TimeoutExpired as e:
+        tail = (e.stderr or b"")[-300:]
+        err = f"timed out after {timeout_s} s: {tail.decode(errors='replace') if isinstance(tail, bytes) else tail}"
     if rank != 0:
         return None
     if not os.path.exists(out):

@@ -41,9 +41,19 @@ def nvlink_kib(index: int):
         out = []
         for v in vals:
             if v.nvmlReturn != 0:
-                return None
+                raise RuntimeError("field not available")
             out.append(int(v.value.ullVal))
         return tuple(out)
+    except Exception:
+        pass
+    try:  # fallback: nvidia-smi's per-link data counters
+        import re
+        import subprocess
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt))
+        return (tx, rx) if (tx or rx) else None
     except Exception:
         return None
 
