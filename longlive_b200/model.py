@@ -249,6 +249,18 @@ class CausalWanModel(nn.Module):
                           sa.local_attn_size, int(c0["global_end_index"].item()),
                           int(c0["local_end_index"].item()))
             c0[_STATE_KEY] = ring
+        elif "_llb_index_tensor" not in c0:
+            # Cache allocated by someone else (the reference's own pipelines): its owner may reset the indices behind
+            # our back - StreamingTrainingPipeline.clear_kv_cache zeroes them (pipeline/streaming_training.py:291-305).
+            # Re-read them: one sync per forward, in a mode where the caller itself does ~150 (.item() per layer).
+            g, l = int(c0["global_end_index"].item()), int(c0["local_end_index"].item())
+            if (g, l) != (ring.global_end, ring.local_end):
+                if (g, l) != (0, 0):
+                    raise RuntimeError(f"kv_cache end indices were changed externally to ({g}, {l}); the ring can only adopt "
+                                       "a reset to zero (it keeps the window rotated, not in logical order)")
+                ring = KvRing(c0["k"].shape[1], sa.sink_size * frame_seqlen, sa.max_attention_size, sa.local_attn_size)
+                c0[_STATE_KEY] = ring
+                c0.pop("_llb_published", None)
         # the pipelines may change these between calls (_set_all_modules_max_attention_size)
         ring.cfg.max_attention_size = int(sa.max_attention_size)
         ring.cfg.local_attn_size = int(sa.local_attn_size)  # the module attribute gates the roll (:231)

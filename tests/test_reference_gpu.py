@@ -163,3 +163,56 @@ def test_full_size_pipeline_vs_reference_flash_attn():
         kerr.append((rel_l2(k, rp.kv_cache1[l]["k"]), rel_l2(v, rp.kv_cache1[l]["v"])))
     print("cache K/V rel-L2 vs the reference's cache (layers 0, 29):", kerr)
     assert max(max(p) for p in kerr) < 3e-2
+
+
+def _streaming_rollout(cls, cfg, gen, noise, prompts):
+    """Three 6-frame chunks continuing one cache (18 frames: the 12-frame window becomes a sub-range of the 33-frame
+    cache), then clear_kv_cache() and a fresh sequence under another prompt."""
+    sch = gen.get_scheduler()
+    table = torch.cat((sch.timesteps.cpu(), torch.tensor([0.0])))
+    steps = table[1000 - torch.tensor([1000, 750, 500, 250])]
+    pipe = cls(denoising_step_list=steps, scheduler=sch, generator=gen, num_frame_per_block=3,
+               same_step_across_blocks=False, last_step_only=False, context_noise=0,
+               local_attn_size=cfg.local_attn_size, slice_last_frames=21)
+    pipe.num_transformer_blocks = cfg.num_layers
+    pipe._initialize_kv_cache(1, torch.bfloat16, torch.device(DEV))
+    pipe._initialize_crossattn_cache(1, torch.bfloat16, torch.device(DEV))
+    outs, ends = [], []
+    with _SeededRandnLike(), torch.no_grad():
+        for call, (start, prompt) in enumerate([(0, 0), (6, 0), (12, 0), (0, 1)]):
+            if call == 3:
+                pipe.clear_kv_cache()
+            torch.manual_seed(100 + call)   # the exit steps are drawn with torch.randint on the device
+            out = pipe.generate_chunk_with_cache(noise[:, 6 * call:6 * call + 6], {"prompt_embeds": prompts[prompt]},
+                                                 current_start_frame=start, requires_grad=False)
+            outs.append(out[0])
+            ends.append((int(pipe.kv_cache1[0]["global_end_index"].item()), int(pipe.kv_cache1[0]["local_end_index"].item())))
+    return torch.cat(outs, 1), ends
+
+
+def test_streaming_training_rollout_vs_reference():
+    """SURVEY 8f rank 4 (gradient-free part): our StreamingTrainingPipeline + CUDA generator vs the reference's class +
+    wrapper + model with flash-attn; and the reference's class driving OUR generator (incl. its clear_kv_cache, which
+    zeroes the end indices of a cache our model has adopted)."""
+    import importlib
+    from oracle import wan_oracle as wo
+    from oracle.make_golden import PIPE_CFG
+    from longlive_b200.pipeline import StreamingTrainingPipeline as Ours
+    ref_shims.use_shipped_copy()
+    cfg = wo.WanConfig(**PIPE_CFG)
+    sd = wo.init_state_dict(cfg, seed=0)
+    wrapper = ref_shims.build_reference_wrapper(cfg, sd, shift=5.0, attention_impl="flash", device=DEV)
+    RefCls = importlib.import_module("pipeline.streaming_training").StreamingTrainingPipeline
+    g = torch.Generator().manual_seed(8)
+    noise = torch.randn(1, 24, 16, 60, 104, generator=g).to(torch.bfloat16).to(DEV)
+    prompts = [wo.synth_prompt_embeds(cfg, 500 + i, 90 + 70 * i).to(DEV) for i in range(2)]
+    r_out, r_ends = _streaming_rollout(RefCls, cfg, wrapper, noise, prompts)
+    ours = _our_generator(cfg, sd)
+    o_out, o_ends = _streaming_rollout(Ours, cfg, ours, noise, prompts)
+    assert o_ends == r_ends == [(6 * 1560, 6 * 1560), (12 * 1560, 12 * 1560), (18 * 1560, 18 * 1560), (6 * 1560, 6 * 1560)]
+    errs = [rel_l2(o_out[:, c:c + 3], r_out[:, c:c + 3]) for c in range(0, 24, 3)]
+    print("streaming-training rollout latents rel-L2 per block vs the reference (flash-attn):", [f"{e:.2e}" for e in errs])
+    assert max(errs) <= 1e-2, errs
+    # the reference's pipeline class around our generator: same results as our class, bit for bit
+    a_out, a_ends = _streaming_rollout(RefCls, cfg, ours, noise, prompts)
+    assert a_ends == r_ends and torch.equal(a_out, o_out), rel_l2(a_out, o_out)
