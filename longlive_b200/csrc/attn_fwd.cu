@@ -52,7 +52,6 @@ namespace llb {
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
-constexpr int kMinSplitTiles = 16;  // stream-K only when an item has at least this many kv tiles
 constexpr int kStages = 5;          // K/V tiles in flight
 constexpr int kAttnSmemBytes = 1024 + 2 * kTileBytes + kStages * kTileBytes + 256;
 
@@ -71,6 +70,7 @@ struct AttnParams {
   float scale_log2;
   const llb_step_params* segs;
   uint8_t* workspace;  // gridDim.x * kWsPerCta bytes, flags zero-initialised once
+  int min_split_tiles;  // the remainder items are split over CTAs only when an item has at least this many kv tiles
   llb_out_shard shard; // n_ranks == 1: single GPU
 };
 
@@ -187,12 +187,12 @@ struct SegIter {
   int ru, ru_end;
   int item, t0, t1;
   bool ok;
-  __device__ __forceinline__ void init(int T_, int n_items, int G_, int c_) {
+  __device__ __forceinline__ void init(int T_, int n_items, int G_, int c_, int min_split) {
     T = T_; G = G_; c = c_;
     rounds = n_items / G;
     rem_items = n_items - rounds * G;
     k = 0;
-    split = (T >= kMinSplitTiles) && rem_items > 0;
+    split = (T >= min_split) && rem_items > 0;
     ru = ru_end = 0;
     if (split) {
       const int gp = min(G, rem_items * kMaxParts);  // CTAs that take part in the remainder
@@ -298,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   KvTileIter kv_it;                                                     \
   kv_it.init(p.segs);                                                   \
   SegIter sg;                                                           \
-  sg.init(kv_it.total_tiles(), p.n_heads * p.n_pairs, gridDim.x, blockIdx.x)
+  sg.init(kv_it.total_tiles(), p.n_heads * p.n_pairs, gridDim.x, blockIdx.x, p.min_split_tiles)
 
   // Register re-distribution: the kernel launches at 168 regs/thread (65536 / 384); the two softmax
   // warpgroups hold a full 128-column S row per thread and take 208, the MMA/TMA warpgroup keeps 88
@@ -767,6 +767,9 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.scale_log2 = scale * 1.4426950408889634f;
   p.segs = seg_dev;
   p.workspace = static_cast<uint8_t*>(workspace);
+  // measured (profiles/r02_attn_pair.md): splitting the 4-tile items of cross-attention costs more in merges than the
+  // idle half round it removes (371 -> 308 TFLOP/s at 4 / 296 at 2)
+  p.min_split_tiles = 16;
   memset(&p.shard, 0, sizeof(p.shard));
   p.shard.n_ranks = 1;
   if (shard != nullptr && shard->n_ranks > 1) {

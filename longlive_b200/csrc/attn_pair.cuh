@@ -144,7 +144,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   KvTileIter kv_it;                                                      \
   kv_it.init(p.segs);                                                    \
   SegIter sg;                                                            \
-  sg.init(kv_it.total_tiles(), p.n_heads * p.n_pairs, n_workers, worker)
+  sg.init(kv_it.total_tiles(), p.n_heads * p.n_pairs, n_workers, worker, p.min_split_tiles)
 
   if (warp >= kMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
