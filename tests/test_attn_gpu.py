@@ -59,7 +59,10 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 64], ids=["v0", "v64_cta_pair"])
+VARIANTS = dict(argvalues=[0, 64, 128], ids=["v0", "v64_cta_pair", "v128_early_qk"])
+
+
+@pytest.mark.parametrize("variant", **VARIANTS)
 @pytest.mark.parametrize("Lq,H,rows,segs", ATTN_CASES)
 def test_attention(Lq, H, rows, segs, variant):
     ops = _ops()
@@ -80,7 +83,7 @@ def test_attention(Lq, H, rows, segs, variant):
     assert torch.equal(out, out2), "second launch on the same workspace differs"
 
 
-@pytest.mark.parametrize("variant", [0, 64], ids=["v0", "v64_cta_pair"])
+@pytest.mark.parametrize("variant", **VARIANTS)
 def test_attention_large_logits(variant):
     """Row maxima that grow tile after tile exercise the lazy O-rescale path."""
     ops = _ops()
@@ -97,3 +100,25 @@ def test_attention_large_logits(variant):
     assert err < 1e-2, f"variant {variant}: rel-L2 {err}"
 
 
+
+
+@pytest.mark.parametrize("variant", **VARIANTS)
+@pytest.mark.parametrize("rows", [2048, 1000, 70])
+def test_attention_outlier_keys(variant, rows):
+    """Keys with a random (log-normal) gain: the row maximum jumps by far more than 2^8 at random positions inside
+    key tiles - in the first and in the second 64 keys of a tile, on an item's first tile and later - so every
+    rescale path runs (O in TMEM; in the early-QK schedule also the already written half of P), with ragged tails
+    (1000 = 7 tiles + 104 keys, 70 = one tile whose second half holds 6 keys)."""
+    ops = _ops()
+    Lq, H = 384, 2
+    g = torch.Generator(device="cpu").manual_seed(11 + rows)
+    q = bf(torch.randn(Lq, H * 128, generator=g) * 2).to(DEV)
+    gain = torch.exp(torch.randn(rows, 1, generator=g) * 1.2)
+    k = bf(torch.randn(rows, H * 128, generator=g) * gain).to(DEV)
+    v = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=[(0, rows)]), DEV)
+    out = ops.attention(q, k, v, sp, n_heads=H, variant=variant)
+    ref = _attn_ref(q, k, v, H, [(0, rows)])
+    assert torch.isfinite(out.float()).all()
+    err = rel_l2(out, ref)
+    assert err < 1e-2, f"variant {variant}: rel-L2 {err}"

@@ -1,0 +1,61 @@
+"""Hand-over timeline of the attention kernel (debug build `make -C longlive_b200/csrc trace`): CTA 0's clock64() stamps
+for the first key tiles of its first item, printed relative to tile `--from`.  Run with LLB200_LIB pointing at the trace build:
+    LLB200_LIB=longlive_b200/libllb200_trace.so python tools/attn_trace.py --variant 128
+"""
+import argparse
+import ctypes as C
+import json
+import os
+
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+os.environ.setdefault("LLB200_LIB", os.path.join(os.path.dirname(__file__), "..", "longlive_b200", "libllb200_trace.so"))
+from longlive_b200 import _lib, ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variant", type=int, default=128)
+    ap.add_argument("--lq", type=int, default=4680)
+    ap.add_argument("--lk", type=int, default=18720)
+    ap.add_argument("--first", type=int, default=20)
+    ap.add_argument("--n", type=int, default=6)
+    args = ap.parse_args()
+    H = 12
+    dev = "cuda"
+    q = torch.randn(args.lq, H * 128, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(args.lk, H * 128, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(args.lk, H * 128, device=dev, dtype=torch.bfloat16)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=[(0, args.lk)]), dev)
+    for _ in range(3):
+        ops.attention(q, k, v, sp, n_heads=H, variant=args.variant)
+    torch.cuda.synchronize()
+    n = 4 * 64 * 16
+    buf = (C.c_ulonglong * n)()
+    lib = _lib.lib()
+    lib.llb_attn_trace_read.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    rc = lib.llb_attn_trace_read(buf, n)
+    assert rc == 0, rc
+    t = torch.tensor(list(buf), dtype=torch.int64).view(4, 64, 16)
+    t0 = int(t[0, args.first, 0])
+    names = {0: ["wait Sb", "Sb ready", "half b done", "Sa ready", "P full", "Sa loaded"],
+             2: ["top", "kv ready", "E1 fired", "QKb issued", "E2 fired", "PV+QKa issued"]}
+    names[1] = names[0]
+    names[3] = names[2]
+    out = []
+    for j in range(args.first, args.first + args.n):
+        for role in (0, 1, 2, 3):
+            for s, nm in enumerate(names[role]):
+                out.append((int(t[role, j, s]) - t0, j, ["softmax0", "softmax1", "issuer0", "issuer1"][role], nm))
+    out.sort()
+    for ts, j, role, nm in out:
+        print(f"{ts:8d}  tile {j:3d}  {role:9s} {nm}")
+    per = (int(t[0, args.first + args.n, 4]) - int(t[0, args.first, 4])) / args.n
+    print(json.dumps({"variant": args.variant, "cycles_per_tile_chain0": per}))
+
+
+if __name__ == "__main__":
+    main()
