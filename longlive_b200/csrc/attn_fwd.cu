@@ -50,7 +50,7 @@
 namespace llb {
 
 // LLB_ATTN_TRACE (debug builds only, tools/attn_trace.py): CTA 0 records clock64() at the hand-over points of the first
-// 64 key tiles of its first item: g_attn_trace[role][tile][slot], role 0 / 1 = softmax chain 0 / 1, 2 / 3 = the chains' MMA issuers.
+// 64 key tiles of its first item: g_attn_trace[role][tile][slot], role 0 / 1 = softmax chain 0 / 1, 2 = the MMA issuer.
 #ifdef LLB_ATTN_TRACE
 __device__ unsigned long long g_attn_trace[4 * 64 * 16];
 #define LLB_TRACE(role, tile, slot)                                                                              \
@@ -246,18 +246,10 @@ struct SegIter {
 // (0 = MUFU only; shipped: 4 - MUFU only and every 8th pair measured the same within noise, profiles/r02_attn_pair.md).  ncu (profiles/r02_attn_ncu_source.md): the softmax warps are ISSUE bound - one warp per
 // scheduler, 40 % of its cycles issuing and 37 % in fixed-latency waits, XU (MUFU) pipe 44 % busy - so the
 // polynomial (12 instructions per pair against 2) is only worth what MUFU time it removes from the chain.
-//
-// kEarly (the "early-QK" schedule): every key tile is produced as two 64-key halves, a = keys 0..63 and b = keys
-// 64..127, in the two 64-column regions X | Y of the chain's 128 S columns.  P(j) (bf16, 64 columns) is written into
-// the region that held S_b(j); the OTHER region is free as soon as the softmax warps have S_a(j) in registers, so
-// QK_b(j+1) is issued right then - half a tile body BEFORE P(j) exists - and only QK_a(j+1) has to queue behind PV(j)
-// (it overwrites P(j)).  The softmax warps work on half b of tile j+1 while the tensor pipe runs PV(j) + QK_a(j+1):
-// the serial chain "P ready -> PV + QK (1024 tensor cycles) -> S ready" of the plain schedule (49 % of the softmax
-// warps' time, profiles/r02_attn_ncu_source.md) disappears without any extra TMEM.  The regions swap roles every tile:
-//   tile parity 0: S_a in X, S_b in Y, P in Y;   parity 1: S_a in Y, S_b in X, P in X.
-// Each half is an online-softmax step of its own (lazy rescale); if half a raises the offset after P_b was stored,
-// P_b is rescaled in TMEM together with O (rare path).
-template <int kPoly, bool kEarly>
+// (An "early-QK" schedule - every key tile as two 64-key halves so that QK_b(j+1) can be issued while P(j) is still being
+// written, one MMA issuer warp per chain - was built in round 2 and measured equal: N = 64 MMAs cost 48 cycles instead of
+// 32 because the Q operand is re-read from shared memory; profiles/r02_attn_early_qk.md, commit 49c72de.)
+template <int kPoly>
 __global__ void __maxnreg__(168)  // = 65536 / 384 threads, rounded down to the allocation unit
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -277,12 +269,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto ofree_bar = [&](int s) { return bar_base + 8u * (10 + s); };
   auto kvfull_bar = [&](int s) { return bar_base + 8u * (12 + s); };
   auto kvempty_bar = [&](int s) { return bar_base + 8u * (12 + kStages + s); };
-  // early-QK schedule only: s_full doubles as "S_b ready"; "S_a ready"; "S_a is in the softmax warps' registers"
-  auto safull_bar = [&](int s) { return bar_base + 8u * (12 + 2 * kStages + s); };
-  auto saloaded_bar = [&](int s) { return bar_base + 8u * (14 + 2 * kStages + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (16 + 2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (14 + 2 * kStages);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (16 + 2 * kStages));
+      reinterpret_cast<volatile uint32_t*>(bar_gen + 8 * (14 + 2 * kStages));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,12 +287,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(pfull_bar(s), 4);  // one arrive per softmax warp
       mbar_init(odone_bar(s), 1);
       mbar_init(ofree_bar(s), 4);
-      mbar_init(safull_bar(s), 1);
-      mbar_init(saloaded_bar(s), 4);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
-      mbar_init(kvempty_bar(s), kEarly ? 2 : 1);  // early-QK schedule: one arrival per chain issuer
+      mbar_init(kvempty_bar(s), 1);
     }
     fence_barrier_init();
   }
@@ -377,138 +364,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
-    } else if (kEarly && (warp == kMmaWarp || warp == kMmaWarp + 2)) {
-      // ------------------------------------------------------------------ MMA issuers, early-QK schedule
-      // One issuing warp PER CHAIN (warp 8: Q tile 0, warp 10: Q tile 1).  tcgen05.mma issue blocks at the tensor
-      // pipe's rate (the queue holds about two instructions, tools/micro/mma_rate.cu), and every mbarrier wait +
-      // tcgen05 fence costs the issuer 150 - 220 cycles even when the barrier completed long ago (tools/attn_trace.py):
-      // a single issuer serving E1_0, E2_0, E1_1, E2_1 in turn left the pipe idle 30 % of the time.  With one issuer
-      // per chain one of them is blocked inside the pipe while the other polls, and no event of a chain ever queues
-      // behind the other chain's.  The chains touch disjoint TMEM; K/V stages are released by BOTH issuers
-      // (kv_empty counts two arrivals).
-      const int tc = (warp == kMmaWarp) ? 0 : 1;
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_qk64 = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);
-      const uint32_t qa = q_base + tc * kTileBytes;
-      const uint32_t t_s = tmem_base + tc * 128;
-      const uint32_t t_o = tmem_base + 256 + tc * 128;
-      // one 64-key half of S into TMEM columns [dcol, dcol + 64) of the chain's S block; half 1 = keys 64..127 = rows
-      // 64.. of both 64-column boxes of the K tile (8 swizzle atoms = 8192 B further)
-      auto issue_qk_half = [&](uint32_t dcol, uint32_t kst, int half) {
-        const uint32_t kb = kst + half * 8192;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          umma_ss(t_s + dcol, umma_desc_kmajor(qa + o), umma_desc_kmajor(kb + o), idesc_qk64, kk != 0);
-        }
-      };
-      // P(j) lives in region preg: keys 64..127 (half b) in its columns [0, 32), keys 0..63 in [32, 64)
-      auto issue_pv = [&](uint32_t preg, uint32_t vst, bool first) {
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t bdesc = umma_desc_mnmajor(vst + kk * 2048, kBoxBytes);
-          const uint32_t pa = t_s + preg + (kk < 4 ? 32 + kk * 8 : (kk - 4) * 8);
-          umma_ts(t_o, pa, bdesc, idesc_pv, (first && kk == 0) ? 0u : 1u);
-        }
-      };
-      // (Handing the pipe over one GROUP of MMAs at a time through a shared-memory lock - which a model of the two
-      // chains says would stagger them and reach the pipe bound - measured 600 - 750 TFLOP/s: the chains share the
-      // 5-stage K/V ring, and a stagger of half a period leaves the leading chain waiting for tiles the lagging one
-      // still holds; profiles/r02_attn_early_qk.md.)
-      LLB_ATTN_INIT_WORK();
-      int stage = 0;
-      uint32_t phase = 0;
-      auto advance = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
-      uint32_t qph = 0, pcnt = 0, oseg = 0;
-      for (; sg.ok; sg.next()) {
-        const int head = sg.item / p.n_pairs;
-        const int q_row0 = (sg.item - head * p.n_pairs) * 256;
-        const bool has1 = q_row0 + 128 < p.Lq;
-        const int nt = sg.t1 - sg.t0;
-        [[maybe_unused]] const bool trace_on = sg.k == 0;
-        if (tc == 1 && !has1) {
-          // this chain has no Q tile in the item: only hand the item's K/V stages back (after the producer has
-          // filled them, so the arrival belongs to the same use of the stage as chain 0's)
-          for (int i = 0; i < 2 * nt; ++i) {
-            mbar_wait(kvfull_bar(stage), phase);
-            if (lane == 0) mbar_arrive(kvempty_bar(stage));
-            __syncwarp();
-            advance();
-          }
-          continue;
-        }
-        // the item's first tile is one N = 128 product: S_a -> X (columns 0..63), S_b -> Y
-        mbar_wait(qfull_bar(tc), qph);
-        qph ^= 1;
-        mbar_wait(kvfull_bar(stage), phase);
-        tc_fence_after();
-        uint32_t kst = kv_base + stage * kTileBytes;
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t o = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-            umma_ss(t_s, umma_desc_kmajor(qa + o), umma_desc_kmajor(kst + o), idesc_qk, kk != 0);
-          }
-          umma_commit(sfull_bar(tc));
-          umma_commit(safull_bar(tc));
-          if (nt == 1) umma_commit(qempty_bar(tc));
-          umma_commit(kvempty_bar(stage));
-        }
-        __syncwarp();
-        advance();
-        // O of the previous item must have been drained before this item's first PV overwrites it
-        mbar_wait(ofree_bar(tc), (oseg & 1) ^ 1);
-        oseg++;
-        for (int j = 0; j < nt; ++j) {
-          const bool more = j + 1 < nt;
-          const bool last_qk = j + 2 == nt;
-          const int vstage = stage;
-          LLB_TRACE(2 + tc, j, 0);
-          mbar_wait(kvfull_bar(stage), phase);
-          const uint32_t vst = kv_base + stage * kTileBytes;
-          advance();
-          int kstage = 0;
-          if (more) {
-            kstage = stage;
-            mbar_wait(kvfull_bar(stage), phase);
-            kst = kv_base + stage * kTileBytes;
-            advance();
-          }
-          const uint32_t reg_b = (j & 1) ? 0u : 64u;  // S_b(j), P(j)
-          const uint32_t reg_a = (j & 1) ? 64u : 0u;  // S_a(j)
-          LLB_TRACE(2 + tc, j, 1);
-          // E1: S_a(j) is in the softmax warps' registers -> S_b(j+1) into the region it left
-          mbar_wait(saloaded_bar(tc), pcnt & 1);
-          tc_fence_after();
-          LLB_TRACE(2 + tc, j, 2);
-          if (more && elect_one()) {
-            issue_qk_half(reg_a, kst, 1);
-            umma_commit(sfull_bar(tc));
-          }
-          __syncwarp();
-          LLB_TRACE(2 + tc, j, 3);
-          // E2: P(j) written -> O += P(j) V_j, then S_a(j+1) over P(j)
-          mbar_wait(pfull_bar(tc), pcnt & 1);
-          pcnt++;
-          tc_fence_after();
-          LLB_TRACE(2 + tc, j, 4);
-          if (elect_one()) {
-            issue_pv(reg_b, vst, j == 0);
-            umma_commit(odone_bar(tc));
-            umma_commit(kvempty_bar(vstage));
-            if (more) {
-              issue_qk_half(reg_b, kst, 0);
-              umma_commit(safull_bar(tc));
-              if (last_qk) umma_commit(qempty_bar(tc));
-              umma_commit(kvempty_bar(kstage));
-            }
-          }
-          __syncwarp();
-          LLB_TRACE(2 + tc, j, 5);
-        }
-      }
-    } else if (!kEarly && warp == kMmaWarp) {
+    } else if (warp == kMmaWarp) {
       // ------------------------------------------------------------------ MMA issuer
       // The whole warp runs this loop (waits included); one elected lane issues the tcgen05 ops.
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);
@@ -544,6 +400,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int q_row0 = (sg.item - head * p.n_pairs) * 256;
         const bool has1 = q_row0 + 128 < p.Lq;
         const int nt = sg.t1 - sg.t0;
+        [[maybe_unused]] const bool trace_on = sg.k == 0;
         // prologue: S_t(first) = Q_t K^T
         mbar_wait(qfull_bar(0), qph0);
         qph0 ^= 1;
@@ -580,6 +437,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
           // V_j
           const int vstage = stage;
+          LLB_TRACE(2, j, 0);
           mbar_wait(kvfull_bar(stage), phase);
           const uint32_t vst = kv_base + stage * kTileBytes;
           advance();
@@ -591,10 +449,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             kst = kv_base + stage * kTileBytes;
             advance();
           }
+          LLB_TRACE(2, j, 1);
           // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
           mbar_wait(pfull_bar(0), pcnt0 & 1);
           pcnt0++;
           tc_fence_after();
+          LLB_TRACE(2, j, 2);
           if (elect_one()) {
             issue_pv(0, vst, j == 0);
             umma_commit(odone_bar(0));
@@ -609,10 +469,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
           }
           __syncwarp();
+          LLB_TRACE(2, j, 3);
           if (has1) {
             mbar_wait(pfull_bar(1), pcnt1 & 1);
             pcnt1++;
             tc_fence_after();
+            LLB_TRACE(2, j, 4);
             if (elect_one()) {
               issue_pv(1, vst, j == 0);
               umma_commit(odone_bar(1));
@@ -625,6 +487,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               }
             }
             __syncwarp();
+            LLB_TRACE(2, j, 5);
           }
         }
       }
@@ -690,114 +553,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
         int row0, valid;
         kv_it.get(row0, valid);
-        if constexpr (kEarly) {
-          const int par = (j - sg.t0) & 1;
-          const uint32_t reg_b = t_s + (par ? 0u : 64u);  // S_b(j); P(j) goes here
-          const uint32_t reg_a = t_s + (par ? 64u : 0u);  // S_a(j)
-          // one 64-key half = one online-softmax step; half b (keys 64..127, ready early) first, then half a
-          auto half = [&](auto masked_tag, auto a_tag) {
-            constexpr bool kMasked = decltype(masked_tag)::value;
-            constexpr bool kA = decltype(a_tag)::value;
-            const uint32_t src = kA ? reg_a : reg_b;
-            const uint32_t pdst = reg_b + (kA ? 32u : 0u);
-            const int nvalid = kA ? valid : valid - 64;  // valid keys of this half (>= 64: all)
-            if constexpr (kMasked && !kA) {
-              if (nvalid <= 0) {  // no key of this half exists: P_b = 0, nothing else changes
-                uint32_t z[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) z[i] = 0u;
-                tmem_st16(pdst, z);
-                tmem_st16(pdst + 16, z);
-                return;
-              }
-            }
-            uint32_t sv[2][32];
-            tmem_ld32(src, sv[0]);
-            tmem_ld32(src + 32, sv[1]);
-            tmem_wait_ld();
-            if constexpr (kA) {
-              // S_a(j) is in registers: the MMA warp may put S_b(j+1) into its region
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(saloaded_bar(t));
-              LLB_TRACE(t, j - sg.t0, 5);
-            }
-            if constexpr (kMasked) {
-#pragma unroll
-              for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (cc * 32 + i >= nvalid) sv[cc][i] = 0xff800000u;  // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-              mx1 = fmaxf(mx1, __uint_as_float(sv[0][16 + i]));
-              mx2 = fmaxf(mx2, __uint_as_float(sv[1][i]));
-              mx3 = fmaxf(mx3, __uint_as_float(sv[1][16 + i]));
-            }
-            const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-            const bool need = (m_new - m_used) * c > 8.0f;
-            if (__any_sync(0xffffffffu, need)) {
-              const float f = ex2_approx((m_used - m_new) * c);  // 0 while m_used = -inf
-              if (j > sg.t0) {
-                // O must be stable: PV(j-1) complete and PV(j) not issued.  S_a(j) ready implies the former (QK_a(j) is
-                // queued behind PV(j-1)); S_b(j) does not, so half b waits for S_a(j) here (the later wait on the
-                // same phase then falls through)
-                if constexpr (!kA) {
-                  mbar_wait(safull_bar(t), cnt & 1);
-                  tc_fence_after();
-                }
-                rescale_o(f);
-              }
-              if constexpr (kA) {
-                // P_b(j) was written against the old offset
-                tmem_wait_st();
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  uint32_t pk[16];
-                  tmem_ld16(reg_b + hh * 16, pk);
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(bf16_lo(pk[i]) * f, bf16_hi(pk[i]) * f);
-                  tmem_st16(reg_b + hh * 16, pk);
-                }
-              }
-              l *= f;
-              m_used = m_new;
-            }
-            const float neg = -m_used * c;
-            const float2 c2 = make_float2(c, c), neg2 = make_float2(neg, neg);
-            float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-            exp_chunk(sv[0], pdst, c2, neg2, la, lb);
-            exp_chunk(sv[1], pdst + 16, c2, neg2, la, lb);
-            la = __fadd2_rn(la, lb);
-            l += la.x + la.y;
-          };
-          LLB_TRACE(t, j - sg.t0, 0);
-          mbar_wait(sfull_bar(t), cnt & 1);
-          tc_fence_after();
-          LLB_TRACE(t, j - sg.t0, 1);
-          if (valid < 128) half(std::true_type{}, std::false_type{});
-          else half(std::false_type{}, std::false_type{});
-          LLB_TRACE(t, j - sg.t0, 2);
-          mbar_wait(safull_bar(t), cnt & 1);
-          tc_fence_after();
-          LLB_TRACE(t, j - sg.t0, 3);
-          if (valid < 64) half(std::true_type{}, std::true_type{});
-          else half(std::false_type{}, std::true_type{});
-          cnt++;
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pfull_bar(t));
-          LLB_TRACE(t, j - sg.t0, 4);
-          continue;
-        }
+        LLB_TRACE(t, j - sg.t0, 0);
         mbar_wait(sfull_bar(t), cnt & 1);
         cnt++;
         tc_fence_after();
+        LLB_TRACE(t, j - sg.t0, 1);
         // The tile body exists twice: full tiles (the common case) carry no masking code at all - as one body with
         // a run-time `valid < 128` test ptxas if-converted the masking into 128 ISETP + 128 SEL executed on EVERY
         // tile, 30 % of the softmax instructions (profiles/r02_attn_ncu_source.md)
@@ -846,6 +606,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull_bar(t));
+        LLB_TRACE(t, j - sg.t0, 4);
       }
       // ---- segment epilogue
       mbar_wait(odone_bar(t), (cnt - 1) & 1);
@@ -951,10 +712,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int kPoly, bool kEarly>
+template <int kPoly>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, int grid, cudaStream_t stream) {
-  LLB_SET_MAX_SMEM((attn_fwd_kernel<kPoly, kEarly>), kAttnSmemBytes);
+  LLB_SET_MAX_SMEM((attn_fwd_kernel<kPoly>), kAttnSmemBytes);
   // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
   // partial-merge flag wait relies on
   cudaLaunchConfig_t cfg = {};
@@ -980,7 +741,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, (attn_fwd_kernel<kPoly, kEarly>), tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPoly>, tq, tk, tv, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -1062,7 +823,5 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     if (rc) return rc;
     return launch_attn_pair(tq, tk64, tv, p, sms, s);
   }
-  // variant bit 7 (128): the early-QK half-tile schedule of the single-CTA kernel
-  if (variant & 128) return launch_attn<4, true>(tq, tk, tv, p, grid, s);
-  return launch_attn<4, false>(tq, tk, tv, p, grid, s);
+  return launch_attn<4>(tq, tk, tv, p, grid, s);
 }

@@ -41,6 +41,20 @@ def main():
     assert rc == 0, rc
     t = torch.tensor(list(buf), dtype=torch.int64).view(4, 64, 16)
     t0 = int(t[0, args.first, 0])
+    if not (args.variant & 128):
+        names0 = ["wait S", "S ready", None, None, "P full"]
+        namesi = ["top", "kv ready", "P0 fired", "PV0+QK0 issued", "P1 fired", "PV1+QK1 issued"]
+        rows = []
+        for j in range(args.first, args.first + args.n):
+            for role, nm in ((0, names0), (1, names0), (2, namesi)):
+                for sidx, x in enumerate(nm):
+                    if x:
+                        rows.append((int(t[role, j, sidx]) - t0, j, ["softmax0", "softmax1", "issuer"][role], x))
+        for ts, j, role, nm in sorted(rows):
+            print(f"{ts:8d}  tile {j:3d}  {role:9s} {nm}")
+        per = (int(t[0, args.first + args.n, 4]) - int(t[0, args.first, 4])) / args.n
+        print(json.dumps({"variant": args.variant, "cycles_per_tile_chain0": per}))
+        return
     names = {0: ["wait Sb", "Sb ready", "half b done", "Sa ready", "P full", "Sa loaded"],
              2: ["top", "kv ready", "E1 fired", "QKb issued", "E2 fired", "PV+QKa issued"]}
     names[1] = names[0]
