@@ -64,8 +64,9 @@ __device__ unsigned long long g_attn_trace[4 * 64 * 16];
 constexpr int kAttnThreads = 384;  // 3 warpgroups: softmax0, softmax1, {MMA, TMA, 2 idle warps}
 constexpr int kTileBytes = 128 * 128 * 2;  // one [128 x 128] bf16 operand tile (two SW128 boxes)
 constexpr int kBoxBytes = 128 * 64 * 2;
-constexpr int kStages = 5;          // K/V tiles in flight
-constexpr int kAttnSmemBytes = 1024 + 2 * kTileBytes + kStages * kTileBytes + 256;
+constexpr int kStages = 4;          // K/V tiles in flight (the fifth tile of shared memory stages the output, below)
+constexpr int kOutStageBytes = 128 * 64 * 2;  // per Q tile: 128 rows x 64 output columns, SWIZZLE_128B, for the TMA store
+constexpr int kAttnSmemBytes = 1024 + 2 * kTileBytes + kStages * kTileBytes + 2 * kOutStageBytes + 256;
 
 // workspace per CTA: partial O [2 tiles][32 col4][128 rows] float4, (m,l) [2][128] float2, flags [2][128]
 constexpr int64_t kWsOBytes = 2ll * 32 * 128 * 16;
@@ -252,14 +253,16 @@ struct SegIter {
 template <int kPoly>
 __global__ void __maxnreg__(168)  // = 65536 / 384 threads, rounded down to the allocation unit
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                const AttnParams p) {
   constexpr int kMmaWarp = 8, kTmaWarp = 9;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t q_base = smem_base;                                   // 2 tiles
   const uint32_t kv_base = q_base + 2 * kTileBytes;                    // kStages tiles
-  const uint32_t bar_base = kv_base + kStages * kTileBytes;
+  const uint32_t ostage_base = kv_base + kStages * kTileBytes;         // 2 x kOutStageBytes
+  const uint32_t bar_base = ostage_base + 2 * kOutStageBytes;
   uint8_t* bar_gen = smem_gen + (bar_base - smem_base);
   auto qfull_bar = [&](int s) { return bar_base + 8u * s; };
   auto qempty_bar = [&](int s) { return bar_base + 8u * (2 + s); };
@@ -280,6 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
     for (int s = 0; s < 2; ++s) {
       mbar_init(qfull_bar(s), 1);
       mbar_init(qempty_bar(s), 1);
@@ -395,12 +399,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t qph0 = 0, qph1 = 0;    // q_full consumer phases
       uint32_t pcnt0 = 0, pcnt1 = 0;  // kv tiles processed per Q tile (p_full phase)
       uint32_t oseg0 = 0, oseg1 = 0;  // segments started per Q tile (o_free phase)
+      {
+        [[maybe_unused]] const bool trace_on = true;
+        LLB_TRACE(2, 0, 9);
+      }
       for (; sg.ok; sg.next()) {
         const int head = sg.item / p.n_pairs;
         const int q_row0 = (sg.item - head * p.n_pairs) * 256;
         const bool has1 = q_row0 + 128 < p.Lq;
         const int nt = sg.t1 - sg.t0;
-        [[maybe_unused]] const bool trace_on = sg.k == 0;
+        [[maybe_unused]] const bool trace_on = sg.T <= 8 ? sg.k < 8 : sg.k == 0;
+        [[maybe_unused]] const int trace_base = sg.T <= 8 ? sg.k * 8 : 0;
+        LLB_TRACE(2, trace_base, 6);
         // prologue: S_t(first) = Q_t K^T
         mbar_wait(qfull_bar(0), qph0);
         qph0 ^= 1;
@@ -424,6 +434,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         __syncwarp();
         advance();
+        LLB_TRACE(2, trace_base, 7);
         // O_t of the previous segment must have been drained by its softmax warps before the
         // first PV of this segment overwrites it
         mbar_wait(ofree_bar(0), (oseg0 & 1) ^ 1);
@@ -432,12 +443,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(ofree_bar(1), (oseg1 & 1) ^ 1);
           oseg1++;
         }
+        LLB_TRACE(2, trace_base, 8);
         for (int j = 0; j < nt; ++j) {
           const bool more = j + 1 < nt;
           const bool last_qk = j + 2 == nt;  // the QK issued in this iteration is the segment's last
           // V_j
           const int vstage = stage;
-          LLB_TRACE(2, j, 0);
+          LLB_TRACE(2, trace_base + j, 0);
           mbar_wait(kvfull_bar(stage), phase);
           const uint32_t vst = kv_base + stage * kTileBytes;
           advance();
@@ -449,12 +461,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             kst = kv_base + stage * kTileBytes;
             advance();
           }
-          LLB_TRACE(2, j, 1);
+          LLB_TRACE(2, trace_base + j, 1);
           // tile 0: O_0 += P_0(j) V_j ; S_0(j+1) = Q_0 K_{j+1}^T
           mbar_wait(pfull_bar(0), pcnt0 & 1);
           pcnt0++;
           tc_fence_after();
-          LLB_TRACE(2, j, 2);
+          LLB_TRACE(2, trace_base + j, 2);
           if (elect_one()) {
             issue_pv(0, vst, j == 0);
             umma_commit(odone_bar(0));
@@ -469,12 +481,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
           }
           __syncwarp();
-          LLB_TRACE(2, j, 3);
+          LLB_TRACE(2, trace_base + j, 3);
           if (has1) {
             mbar_wait(pfull_bar(1), pcnt1 & 1);
             pcnt1++;
             tc_fence_after();
-            LLB_TRACE(2, j, 4);
+            LLB_TRACE(2, trace_base + j, 4);
             if (elect_one()) {
               issue_pv(1, vst, j == 0);
               umma_commit(odone_bar(1));
@@ -487,7 +499,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               }
             }
             __syncwarp();
-            LLB_TRACE(2, j, 5);
+            LLB_TRACE(2, trace_base + j, 5);
           }
         }
       }
@@ -548,16 +560,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int grow = q_row0 + t * 128 + row_in_tile;
       float m_used = -INFINITY;
       float l = 0.f;
-      [[maybe_unused]] const bool trace_on = sg.k == 0 && q == 0;
+      [[maybe_unused]] const bool trace_on = (sg.T <= 8 ? sg.k < 8 : sg.k == 0) && q == 0;
+      [[maybe_unused]] const int trace_base = sg.T <= 8 ? sg.k * 8 : 0;
       kv_it.seek(sg.t0);
       for (int j = sg.t0; j < sg.t1; ++j, kv_it.next()) {
         int row0, valid;
         kv_it.get(row0, valid);
-        LLB_TRACE(t, j - sg.t0, 0);
+        LLB_TRACE(t, trace_base + j - sg.t0, 0);
         mbar_wait(sfull_bar(t), cnt & 1);
         cnt++;
         tc_fence_after();
-        LLB_TRACE(t, j - sg.t0, 1);
+        LLB_TRACE(t, trace_base + j - sg.t0, 1);
         // The tile body exists twice: full tiles (the common case) carry no masking code at all - as one body with
         // a run-time `valid < 128` test ptxas if-converted the masking into 128 ISETP + 128 SEL executed on EVERY
         // tile, 30 % of the softmax instructions (profiles/r02_attn_ncu_source.md)
@@ -606,11 +619,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull_bar(t));
-        LLB_TRACE(t, j - sg.t0, 4);
+        LLB_TRACE(t, trace_base + j - sg.t0, 4);
       }
       // ---- segment epilogue
       mbar_wait(odone_bar(t), (cnt - 1) & 1);
       tc_fence_after();
+      LLB_TRACE(t, trace_base + sg.t1 - sg.t0 - 1, 6);
       const bool tail_part = sg.in_remainder() && sg.t0 > 0;     // earlier kv tiles live in CTA blockIdx.x - 1
       const bool head_part = sg.in_remainder() && sg.t1 < sg.T;  // later kv tiles live in CTA blockIdx.x + 1
       const bool row_ok = grow < p.Lq;
@@ -655,6 +669,61 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                static_cast<int64_t>(grow - r * p.shard.rows_per_rank) * p.shard.ld_out + p.shard.head_col0 +
                head * p.shard.head_col_stride;
       }
+      // Final output of a single-GPU launch: through shared memory and a TMA store.  Written straight from registers a
+      // thread owns a ROW, so a warp's 16-byte stores hit 32 different sectors: draining one O tile took 5600 - 7400 cycles
+      // of LSU time (tools/attn_trace.py), a quarter of a cross-attention launch.  Staged as two [128 x 64] SWIZZLE_128B
+      // boxes per Q tile, the store is two bulk tensor copies; rows beyond Lq are clipped by the tensor map.
+      const bool staged = !tail_part && p.shard.n_ranks == 1;
+      if (staged) {
+        const uint32_t obuf = ostage_base + t * kOutStageBytes;
+        const uint32_t orow_s = obuf + row_in_tile * 128;
+        const bool leader = (warp & 3) == 0 && lane == 0;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int c2i = 0; c2i < 2; ++c2i) {
+            const int cc = hh * 2 + c2i;
+            uint32_t ov[32];
+            tmem_ld32(t_o + cc * 32, ov);
+            tmem_wait_ld();
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(ov[i]) * a_own;
+            if (wo_in != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 x = ld_cg_f4(wo_in + (cc * 8 + i) * 128);
+                o[4 * i] += x.x * a_oth;
+                o[4 * i + 1] += x.y * a_oth;
+                o[4 * i + 2] += x.z * a_oth;
+                o[4 * i + 3] += x.w * a_oth;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[c2i * 16 + i] = pack_bf16x2(o[2 * i], o[2 * i + 1]);
+          }
+          // the previous bulk store out of this buffer (first half, or the previous item) must have read it
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t a = orow_s + static_cast<uint32_t>((ch ^ (row_in_tile & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]),
+                         "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+          if (leader) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_o)),
+                         "r"(obuf), "r"(head * 128 + hh * 64), "r"(q_row0 + t * 128)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t ov[32];
@@ -691,6 +760,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+      }
       if (flag_in != nullptr) st_release_u32(flag_in, 0u);  // consume: ready for the next launch
       if (tail_part && row_ok) {
         reinterpret_cast<float2*>(wsb_out + kWsOBytes)[ws_row] = make_float2(m_used, l);
@@ -701,7 +771,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(ofree_bar(t));
+      LLB_TRACE(t, trace_base + sg.t1 - sg.t0 - 1, 7);
     }
+    // the bulk stores of this thread are complete (and have released the staging buffer) before the CTA exits
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -713,7 +786,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 template <int kPoly>
-static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                        const AttnParams& p, int grid, cudaStream_t stream) {
   LLB_SET_MAX_SMEM((attn_fwd_kernel<kPoly>), kAttnSmemBytes);
   // cooperative launch: the runtime guarantees (or refuses) co-residency of all CTAs, which the
@@ -741,7 +814,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPoly>, tq, tk, tv, p));
+  LLB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<kPoly>, tq, tk, tv, to, p));
   LLB_LAUNCH_CHECK("attn_fwd_kernel");
   return LLB_OK;
 }
@@ -823,5 +896,11 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     if (rc) return rc;
     return launch_attn_pair(tq, tk64, tv, p, sms, s);
   }
-  return launch_attn<4>(tq, tk, tv, p, grid, s);
+  // output map for the staged TMA store (single-GPU launches; the head-parallel path stores to peer memory directly)
+  CUtensorMap to = tq;
+  if (p.shard.n_ranks == 1) {
+    rc = make_tmap_2d_bf16(&to, out, Lq, static_cast<uint64_t>(n_heads) * 128, ldo, 128, 64);
+    if (rc) return rc;
+  }
+  return launch_attn<4>(tq, tk, tv, to, p, grid, s);
 }

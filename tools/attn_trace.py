@@ -40,35 +40,24 @@ def main():
     rc = lib.llb_attn_trace_read(buf, n)
     assert rc == 0, rc
     t = torch.tensor(list(buf), dtype=torch.int64).view(4, 64, 16)
-    t0 = int(t[0, args.first, 0])
-    if not (args.variant & 128):
-        names0 = ["wait S", "S ready", None, None, "P full"]
-        namesi = ["top", "kv ready", "P0 fired", "PV0+QK0 issued", "P1 fired", "PV1+QK1 issued"]
-        rows = []
-        for j in range(args.first, args.first + args.n):
-            for role, nm in ((0, names0), (1, names0), (2, namesi)):
-                for sidx, x in enumerate(nm):
-                    if x:
-                        rows.append((int(t[role, j, sidx]) - t0, j, ["softmax0", "softmax1", "issuer"][role], x))
-        for ts, j, role, nm in sorted(rows):
-            print(f"{ts:8d}  tile {j:3d}  {role:9s} {nm}")
+    names0 = ["wait S", "S ready", None, None, "P full", None, "O complete", "O drained"]
+    namesi = ["top", "kv ready", "P0 fired", "PV0+QK0 issued", "P1 fired", "PV1+QK1 issued", "item start", "first QK issued",
+              "O free", "issuer enters its loop (kernel start + setup)"]
+    short = (args.lk + 127) // 128 <= 8
+    tiles = range(0, 16) if short else range(args.first, args.first + args.n)
+    t0 = min(int(x) for x in t[:3, tiles.start].flatten() if int(x) > 0)
+    rows = []
+    for j in tiles:
+        for role, nm in ((0, names0), (1, names0), (2, namesi)):
+            for sidx, x in enumerate(nm):
+                if x and int(t[role, j, sidx]) > 0:
+                    lab = f"item {j // 8} tile {j % 8}" if short else f"tile {j:3d}"
+                    rows.append((int(t[role, j, sidx]) - t0, lab, ["softmax0", "softmax1", "issuer"][role], x))
+    for ts, lab, role, nm in sorted(rows):
+        print(f"{ts:8d}  {lab}  {role:9s} {nm}")
+    if not short:
         per = (int(t[0, args.first + args.n, 4]) - int(t[0, args.first, 4])) / args.n
         print(json.dumps({"variant": args.variant, "cycles_per_tile_chain0": per}))
-        return
-    names = {0: ["wait Sb", "Sb ready", "half b done", "Sa ready", "P full", "Sa loaded"],
-             2: ["top", "kv ready", "E1 fired", "QKb issued", "E2 fired", "PV+QKa issued"]}
-    names[1] = names[0]
-    names[3] = names[2]
-    out = []
-    for j in range(args.first, args.first + args.n):
-        for role in (0, 1, 2, 3):
-            for s, nm in enumerate(names[role]):
-                out.append((int(t[role, j, s]) - t0, j, ["softmax0", "softmax1", "issuer0", "issuer1"][role], nm))
-    out.sort()
-    for ts, j, role, nm in out:
-        print(f"{ts:8d}  tile {j:3d}  {role:9s} {nm}")
-    per = (int(t[0, args.first + args.n, 4]) - int(t[0, args.first, 4])) / args.n
-    print(json.dumps({"variant": args.variant, "cycles_per_tile_chain0": per}))
 
 
 if __name__ == "__main__":
