@@ -902,5 +902,7 @@ extern "C" int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     rc = make_tmap_2d_bf16(&to, out, Lq, static_cast<uint64_t>(n_heads) * 128, ldo, 128, 64);
     if (rc) return rc;
   }
+  // kPoly = 4: A/B in the full pipeline under the power cap (profiles/r02_poly_ab.txt): MUFU only runs at a higher clock
+  // (1650 vs 1620 MHz) but slower per clock, 95.2 vs 95.9 FPS; every 8th pair 95.2, every 2nd 93.2
   return launch_attn<4>(tq, tk, tv, to, p, grid, s);
 }
