@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B on one box under the power cap: share of exp2 evaluated on the FMA pipe in the attention kernel
+# A/B on one box under the power cap: mbarrier.try_wait suspend-time hint
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 run() { # name, env...
@@ -11,9 +11,7 @@ d = json.load(open(f'gpurun_out/b4_{sys.argv[1]}.json'))
 print(sys.argv[1], round(d['value'], 2), 'FPS', d['clocks']['sm_mhz'], 'MHz', round(d['value'] / d['clocks']['sm_mhz'] * 1000, 2), 'FPS/GHz', 'steady', round(d['config']['steady_state_video_fps'], 2), 'attn TF', round(d['roofline']['achieved']))
 PY
 }
-run poly4 LLB_ATTN_POLY=4
-run poly0 LLB_ATTN_POLY=0
-run poly8 LLB_ATTN_POLY=8
-run poly2 LLB_ATTN_POLY=2
-run poly4b LLB_ATTN_POLY=4
-run poly0b LLB_ATTN_POLY=0
+run base LLB_X=0
+run hint LLB200_LIB=longlive_b200/libllb200_hint.so
+run base2 LLB_X=0
+run hint2 LLB200_LIB=longlive_b200/libllb200_hint.so
