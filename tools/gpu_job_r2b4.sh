@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B on one box under the power cap: mbarrier.try_wait suspend-time hint
+# A/B on one box under the power cap: tile mode of the N = 1536 GEMMs (o, cross-q, cross-o, ffn.2) inside the full pipeline
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 run() { # name, env...
@@ -8,10 +8,12 @@ run() { # name, env...
   python - "$name" <<'PY'
 import json, sys
 d = json.load(open(f'gpurun_out/b4_{sys.argv[1]}.json'))
-print(sys.argv[1], round(d['value'], 2), 'FPS', d['clocks']['sm_mhz'], 'MHz', round(d['value'] / d['clocks']['sm_mhz'] * 1000, 2), 'FPS/GHz', 'steady', round(d['config']['steady_state_video_fps'], 2), 'attn TF', round(d['roofline']['achieved']))
+print(sys.argv[1], round(d['value'], 2), 'FPS', d['clocks']['sm_mhz'], 'MHz', round(d['value'] / d['clocks']['sm_mhz'] * 1000, 2), 'FPS/GHz', 'steady', round(d['config']['steady_state_video_fps'], 2))
 PY
 }
 run base LLB_X=0
-run hint LLB200_LIB=longlive_b200/libllb200_hint.so
+run pair256 LLB_GEMM_TILE_1536=1,256
+run pair192 LLB_GEMM_TILE_1536=1,192
+run single256 LLB_GEMM_TILE_1536=0,256
+run single128 LLB_GEMM_TILE_1536=0,128
 run base2 LLB_X=0
-run hint2 LLB200_LIB=longlive_b200/libllb200_hint.so
