@@ -159,18 +159,6 @@ int llb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
                   int64_t ld_gate, int rows_per_gate, int gate_row0, const void* res, int64_t ld_res,
                   void* stream);
 
-/* Stream-K mode of llb_gemm_bf16 (chosen by the library per shape, e.g. the N = 1536 projections of the block
- * - causal_model.py:364, 408; model.py:172, 193 - whose 256 x 256 pair tiles would otherwise fill 1.54 waves): every CTA
- * (pair) gets one contiguous range of the flattened (tile, k-block) space; a tile cut between two workers is completed
- * by the one holding its first k-blocks, which adds the other's fp32 partial from this workspace.  The caller registers
- * one workspace per device: llb_gemm_streamk_workspace_bytes() bytes, 256-byte aligned, ZERO-initialised once (the
- * flags in it are reset by their reader, so captured graphs replay).  Launches that share a device must be stream
- * ordered (one stream, or several streams that never run GEMMs concurrently).  Without a registered workspace, or with
- * LLB_GEMM_STREAMK=0, the mode is never chosen; results are bit-identical either way for the whole tiles and differ by
- * fp32 summation order (one extra partial sum) in the cut tiles. */
-int64_t llb_gemm_streamk_workspace_bytes(void);
-int llb_gemm_set_streamk_workspace(void* workspace, int64_t bytes);
-
 /* Split-K form for skinny problems (the umT5 encoder's N = 4096 projections at 128-256 token rows stream 33-84 MB of
  * weights through only 64 CTAs otherwise): k_splits partial products are written as fp32 to `workspace`
  * (k_splits * M * N floats, caller-owned) and a second launch sums them and applies the epilogue

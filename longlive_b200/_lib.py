@@ -126,8 +126,6 @@ _PROTOS = {
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
          C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
     ),
-    "llb_gemm_streamk_workspace_bytes": (C.c_int64, []),
-    "llb_gemm_set_streamk_workspace": (C.c_int, [C.c_void_p, C.c_int64]),
     "llb_gemm_bf16_splitk": (
         C.c_int,
         [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

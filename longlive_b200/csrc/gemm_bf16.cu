@@ -77,63 +77,6 @@ struct GemmParams {
                                  // and its fp32 partial goes to slice ks of the workspace `out` points at
   const float* a_scale;  // fp8 path: per-row activation scale [M]
   const float* w_scale;  // fp8 path: per-output-channel weight scale [N]
-  // stream-K (see GemmSegIter): fp32 partial tiles, one kSkSlotBytes slot per CTA, and one flag per epilogue warp
-  int stream_k;
-  float* sk_ws;
-  uint32_t* sk_flags;
-};
-
-// Stream-K.  With 256 x 256 pair tiles the N = 1536 shapes of the block have 114 tiles for 74 CTA pairs: 1.54 waves, the
-// second one half empty - which is why they ran on 128 x 192 single tiles (2.0 waves exactly) although those move 1.5x
-// more bytes per flop.  In stream-K mode the flattened (tile, k-block) space is cut into one contiguous range per worker
-// instead: a range is [tail of a tile] [whole tiles] [head of a tile].  The worker that owns a tile's TAIL (always the
-// first thing it does) publishes its raw fp32 accumulator to its workspace slot; the worker that owns the HEAD (the last
-// thing the previous worker does) adds that partial to its own accumulator and runs the normal epilogue, so nobody waits
-// in practice.  A tile spans at most two workers (the host only picks the mode when a range is at least one tile long).
-// Flags are per epilogue warp (warp w of the reader consumes exactly what warp w of the writer produced) and are reset
-// by their reader, which keeps the launch replayable inside a CUDA graph.
-constexpr int kSkSlotBytes = 128 * 256 * 4;  // one CTA's 128 x BN fp32 accumulator, BN <= 256
-struct GemmSeg {
-  int tile;      // output tile; classic mode: also encodes the k-split
-  int kb0, nkb;  // k-blocks [kb0, kb0 + nkb)
-  int kind;      // 0 whole tile, 1 tail (publish the partial), 2 head (merge the next worker's partial)
-};
-struct GemmSegIter {
-  int cursor, end, step, tiles_mn, nkb_total, kb_per_split;
-  bool sk;
-  __device__ __forceinline__ void init(const GemmParams& p, int worker, int num_workers, int tiles_mn_, int nkb_total_) {
-    tiles_mn = tiles_mn_;
-    nkb_total = nkb_total_;
-    kb_per_split = p.kb_per_split;
-    sk = p.stream_k != 0;
-    if (sk) {
-      const long long U = static_cast<long long>(tiles_mn) * nkb_total;
-      cursor = static_cast<int>(U * worker / num_workers);
-      end = static_cast<int>(U * (worker + 1) / num_workers);
-      step = 0;
-    } else {
-      cursor = worker;
-      end = tiles_mn * p.k_splits;
-      step = num_workers;
-    }
-  }
-  __device__ __forceinline__ bool next(GemmSeg& sg) {
-    if (cursor >= end) return false;
-    if (sk) {
-      sg.tile = cursor / nkb_total;
-      sg.kb0 = cursor - sg.tile * nkb_total;
-      sg.nkb = min(nkb_total - sg.kb0, end - cursor);
-      sg.kind = sg.kb0 > 0 ? 1 : (sg.nkb < nkb_total ? 2 : 0);
-      cursor += sg.nkb;
-    } else {
-      sg.tile = cursor;
-      sg.kb0 = (cursor / tiles_mn) * kb_per_split;
-      sg.nkb = min(kb_per_split, nkb_total - sg.kb0);
-      sg.kind = 0;
-      cursor += step;
-    }
-    return true;
-  }
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -191,6 +134,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int worker = kPair ? (blockIdx.x >> 1) : blockIdx.x;
   const int num_workers = kPair ? (gridDim.x >> 1) : gridDim.x;
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = tiles_mn * p.k_splits;
   constexpr int kKElems = kFp8 ? 128 : kBK;  // elements per k-block (always 128 bytes)
   const int num_kb_total = (p.K + kKElems - 1) / kKElems;
 
@@ -232,16 +176,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      GemmSegIter sit;
-      sit.init(p, worker, num_workers, tiles_mn, num_kb_total);
-      GemmSeg sg;
-      while (sit.next(sg)) {
-        const int tmn = sg.tile % tiles_mn;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
         const int m_idx = tmn % p.num_m_tiles;
         const int n_idx = tmn / p.num_m_tiles;
         const int a_row = kPair ? (m_idx * 2 + static_cast<int>(cta_rank)) * kBM : m_idx * kBM;
         const int b_row = n_idx * BN + (kPair ? static_cast<int>(cta_rank) * (BN / 2) : 0);
-        for (int kb = sg.kb0; kb < sg.kb0 + sg.nkb; ++kb) {
+        const int kb0 = ks * p.kb_per_split;
+        const int num_kb = min(p.kb_per_split, num_kb_total - kb0);
+        for (int kb = kb0; kb < kb0 + num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = stage_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kStageA;
@@ -269,16 +212,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       constexpr uint32_t idesc = kFp8 ? umma_idesc_e4m3(kMmaM, BN) : umma_idesc_bf16(kMmaM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      GemmSegIter sit;
-      sit.init(p, worker, num_workers, tiles_mn, num_kb_total);
-      GemmSeg sg;
-      for (int it = 0; sit.next(sg); ++it) {
+      int it = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const int num_kb = sg.nkb;
+        const int num_kb = min(p.kb_per_split, num_kb_total - (tile / tiles_mn) * p.kb_per_split);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -326,25 +267,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool has_mul = epi == LLB_EPI_BIAS_MUL;
     const bool has_res = (epi == LLB_EPI_BIAS_GATE_RES || epi == LLB_EPI_BIAS_RES || has_mul);
     const bool has_gate = epi == LLB_EPI_BIAS_GATE_RES;
-    // stream-K: this warp's part of this CTA's partial slot / of the slot it merges from (the next worker, same rank)
-    constexpr int kSkWarpFloat4 = (BN / 64) * 8 * 32;
-    float4* sk_out = nullptr;
-    const float4* sk_in = nullptr;
-    uint32_t* sk_flag_out = nullptr;
-    uint32_t* sk_flag_in = nullptr;
-    if (p.stream_k) {
-      const int64_t slot_f4 = kSkSlotBytes / 16;
-      const int nxt = static_cast<int>(blockIdx.x) + (kPair ? 2 : 1);
-      sk_out = reinterpret_cast<float4*>(p.sk_ws) + blockIdx.x * slot_f4 + (warp - 2) * kSkWarpFloat4 + lane;
-      sk_in = reinterpret_cast<const float4*>(p.sk_ws) + nxt * slot_f4 + (warp - 2) * kSkWarpFloat4 + lane;
-      sk_flag_out = p.sk_flags + blockIdx.x * kEpiWarps + (warp - 2);
-      sk_flag_in = p.sk_flags + nxt * kEpiWarps + (warp - 2);
-    }
-    GemmSegIter sit;
-    sit.init(p, worker, num_workers, tiles_mn, num_kb_total);
-    GemmSeg sg;
-    for (int it = 0; sit.next(sg); ++it) {
-      const int tile = sg.tile;
+    int it = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
       const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
       const int m_idx = tmn % p.num_m_tiles;
       const int n_idx = tmn / p.num_m_tiles;
@@ -365,24 +289,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
       __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (sg.kind == 2) {
-        // the tile's tail was the first thing the next worker computed: normally long since published
-        if (lane == 0) {
-          uint32_t spins = 0;
-          uint64_t t_start = 0;
-          uint32_t f;
-          for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(sk_flag_in) : "memory");
-            if (f != 0u) break;
-            if ((++spins & 0xfffu) == 0) {
-              const uint64_t now = global_timer_ns();
-              if (t_start == 0) t_start = now;
-              else if (now - t_start > LLB_WAIT_TIMEOUT_NS) __trap();
-            }
-          }
-        }
-        __syncwarp();
-      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * 32;
       if constexpr (BN == 256 && !kFp8) {
         if (epi == LLB_EPI_GEGLU_BF16) {
@@ -436,37 +342,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (lane == 0) {
             if constexpr (kPair) mbar_arrive_cluster(tempty_lead0 + 8u * acc);
             else mbar_arrive(tempty_bar(acc));
-          }
-        }
-        if (sg.kind == 1) {
-          // stream-K tail: raw accumulator -> this CTA's slot, [slab][4-column group][row]: a warp stores 512 contiguous bytes
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            sk_out[(c * 8 + g) * 32] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-          if (c == BN / 64 - 1) {
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sk_flag_out), "r"(1u) : "memory");
-          }
-          continue;
-        }
-        if (sg.kind == 2) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float4 x;
-            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                         : "l"(sk_in + (c * 8 + g) * 32)
-                         : "memory");
-            v[4 * g] = __float_as_uint(__uint_as_float(v[4 * g]) + x.x);
-            v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + x.y);
-            v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + x.z);
-            v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + x.w);
-          }
-          if (c == BN / 64 - 1) {
-            __syncwarp();
-            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sk_flag_in), "r"(0u) : "memory");
           }
         }
         if (epi == LLB_EPI_BIAS_F32) {
@@ -607,7 +482,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   LLB_CHECK_ARG(sms > 0, "no CUDA device");
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int workers = kPair ? sms / 2 : sms;
-  const int grid = (tiles < workers || p.stream_k ? (p.stream_k ? workers : tiles) : workers) * (kPair ? 2 : 1);
+  const int grid = (tiles < workers ? tiles : workers) * (kPair ? 2 : 1);
   LLB_CUDA(launch_ex(gemm_bf16_kernel<BN, kFp8, kPair>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
                      kPair ? 2 : 1, true, ta, tb, p));
   LLB_LAUNCH_CHECK("gemm_bf16_kernel");
@@ -631,33 +506,6 @@ static int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, con
 }
 
 }  // namespace llb
-
-// Stream-K workspace: registered once per device by the host side (longlive_b200/ops.py allocates it with torch and
-// zeroes it); without one the stream-K mode is simply never chosen.
-namespace llb {
-struct SkWorkspace { void* base; int64_t bytes; };
-static SkWorkspace g_sk_ws[64] = {};
-static int64_t sk_workspace_bytes_needed(int sms) {
-  return 4096 /* flags: sms x 8 warps x 4 B */ + static_cast<int64_t>(sms) * kSkSlotBytes;
-}
-}  // namespace llb
-
-extern "C" int64_t llb_gemm_streamk_workspace_bytes(void) {
-  const int sms = llb::device_sm_count();
-  return llb::sk_workspace_bytes_needed(sms > 0 ? sms : 148);
-}
-
-extern "C" int llb_gemm_set_streamk_workspace(void* ws, int64_t bytes) {
-  using namespace llb;
-  int dev = 0;
-  LLB_CUDA(cudaGetDevice(&dev));
-  LLB_CHECK_ARG(dev >= 0 && dev < 64, "gemm: device ordinal %d out of range", dev);
-  LLB_CHECK_ARG(ws == nullptr || ((reinterpret_cast<uintptr_t>(ws) & 255) == 0 && bytes >= llb_gemm_streamk_workspace_bytes()),
-                "gemm: the stream-K workspace must be 256-byte aligned, zero-initialised and llb_gemm_streamk_workspace_bytes() long");
-  g_sk_ws[dev].base = ws;
-  g_sk_ws[dev].bytes = ws ? bytes : 0;
-  return LLB_OK;
-}
 
 static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, void* out,
                      int64_t ldo, int M, int N, int K, int epilogue, const void* bias, const void* gate,
@@ -698,18 +546,9 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   const int sms = device_sm_count() > 0 ? device_sm_count() : 148;
   int bn = 64;
   bool pair = false;
-  bool stream_k = false;
-  // stream-K needs the registered workspace; LLB_GEMM_STREAMK=0 switches it off (A/B runs)
-  int dev = 0;
-  cudaGetDevice(&dev);
-  static const bool sk_env = getenv("LLB_GEMM_STREAMK") == nullptr || atoi(getenv("LLB_GEMM_STREAMK")) != 0;
-  const bool sk_ok = sk_env && !fp8 && k_splits == 1 && epilogue != LLB_EPI_GEGLU_BF16 && epilogue != LLB_EPI_BIAS_F32 &&
-                     dev >= 0 && dev < 64 && g_sk_ws[dev].base != nullptr &&
-                     g_sk_ws[dev].bytes >= sk_workspace_bytes_needed(sms);
   if (N > 64) {
     static const double kCostBf16[2][3] = {{330, 388, 446}, {275, 325, 420}};  // [pair][bn 128/192/256]
     static const double kCostFp8[2][3] = {{383, 475, 567}, {375, 475, 600}};
-    const int nkb = (K + (fp8 ? 128 : kBK) - 1) / (fp8 ? 128 : kBK);
     double best = 1e30;
     for (int pr = 0; pr < 2; ++pr) {
       const int workers = pr ? sms / 2 : sms;
@@ -718,16 +557,8 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
         const int cand = 128 + 64 * i;
         const int tiles = m_tiles * ((N + cand - 1) / cand) * k_splits;
         const int waves = (tiles + workers - 1) / workers;
-        const double per_kb = fp8 ? kCostFp8[pr][i] : kCostBf16[pr][i];
-        const double cost = static_cast<double>(waves) * (nkb / k_splits) * per_kb;
-        if (cost < best) { best = cost; bn = cand; pair = pr != 0; stream_k = false; }
-        // stream-K: every worker gets ceil(units / workers) k-blocks plus the hand-over of one partial tile (publish or
-        // merge 128 x BN fp32 through L2: about four k-blocks' worth); a range must be at least one tile long
-        const long long units = static_cast<long long>(tiles) * nkb;
-        if (sk_ok && units / workers >= nkb) {
-          const double cost_sk = (static_cast<double>((units + workers - 1) / workers) + 4.0) * per_kb;
-          if (cost_sk < 0.97 * best) { best = cost_sk; bn = cand; pair = pr != 0; stream_k = true; }
-        }
+        const double cost = waves * (fp8 ? kCostFp8[pr][i] : kCostBf16[pr][i]);
+        if (cost < best) { best = cost; bn = cand; pair = pr != 0; }
       }
     }
   }
@@ -743,30 +574,9 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   const char* force = getenv("LLB_GEMM_TILE");
   if (force != nullptr && N > 64 && epilogue != LLB_EPI_GEGLU_BF16) {
     int fp = 0, fb = 0;
-    int fs = 0;
-    const int nf = sscanf(force, "%d,%d,%d", &fp, &fb, &fs);  // "<pair>,<bn>[,<stream-K 0|1>]"
-    if (nf >= 2 && (fb == 128 || fb == 192 || fb == 256)) {
+    if (sscanf(force, "%d,%d", &fp, &fb) == 2 && (fb == 128 || fb == 192 || fb == 256)) {
       pair = fp != 0;
       bn = fb;
-      stream_k = false;
-      if (nf == 3 && fs != 0 && sk_ok) {
-        const int nkb = (K + kBK - 1) / kBK;
-        const long long tiles = static_cast<long long>(pair ? (M + 2 * kBM - 1) / (2 * kBM) : (M + kBM - 1) / kBM) *
-                                ((N + bn - 1) / bn);
-        stream_k = tiles * nkb / (pair ? sms / 2 : sms) >= nkb;
-      }
-    }
-  }
-  if (epilogue == LLB_EPI_GEGLU_BF16) stream_k = false;
-
-  // experiment: LLB_GEMM_TILE_1536="<pair>,<bn>" overrides the choice for the N = 1536 shapes only
-  if (N == 1536 && epilogue != LLB_EPI_GEGLU_BF16) {
-    static const char* f1536 = getenv("LLB_GEMM_TILE_1536");
-    int fp = 0, fb = 0;
-    if (f1536 != nullptr && sscanf(f1536, "%d,%d", &fp, &fb) == 2 && (fb == 128 || fb == 192 || fb == 256)) {
-      pair = fp != 0;
-      bn = fb;
-      stream_k = false;
     }
   }
 
@@ -784,9 +594,6 @@ static int gemm_impl(bool fp8, const void* A, int64_t lda, const void* W, int64_
   p.w_scale = w_scale;
   p.k_splits = k_splits;
   p.kb_per_split = ((K + (fp8 ? 128 : kBK) - 1) / (fp8 ? 128 : kBK) + k_splits - 1) / k_splits;
-  p.stream_k = stream_k ? 1 : 0;
-  p.sk_flags = stream_k ? static_cast<uint32_t*>(g_sk_ws[dev].base) : nullptr;
-  p.sk_ws = stream_k ? reinterpret_cast<float*>(static_cast<uint8_t*>(g_sk_ws[dev].base) + 4096) : nullptr;
 
   CUtensorMap ta, tb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

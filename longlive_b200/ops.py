@@ -49,23 +49,6 @@ def launch_count() -> int:
 
 
 # ------------------------------------------------------------------------------------------------
-_GEMM_SK_WS = {}
-
-
-def _ensure_streamk_workspace(dev: torch.device) -> None:
-    """Registers the per-device stream-K workspace of llb_gemm_bf16 on first use (never while a CUDA graph is being
-    captured: an allocation there would belong to the graph's pool; the eager forward that precedes every capture has
-    registered it by then, and without a workspace the library simply does not pick the stream-K mode)."""
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    if idx in _GEMM_SK_WS or torch.cuda.is_current_stream_capturing():
-        return
-    with torch.cuda.device(idx):
-        n = int(_lib.lib().llb_gemm_streamk_workspace_bytes())
-        ws = torch.zeros(n, dtype=torch.uint8, device=dev)
-        _lib.check(_lib.lib().llb_gemm_set_streamk_workspace(ws.data_ptr(), n), "llb_gemm_set_streamk_workspace")
-    _GEMM_SK_WS[idx] = ws
-
-
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
          epilogue: int = EPI_BIAS, out: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, rows_per_gate: int = 0, gate_row0: int = 0,
@@ -83,7 +66,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     for t, n in ((bias, "bias"), (gate, "gate"), (res, "res")):
         if t is not None:
             _req(t, n)
-    _ensure_streamk_workspace(a.device)
     rc = _lib.lib().llb_gemm_bf16(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
         M, N, K, epilogue, _ptr(bias), _ptr(gate), gate.stride(0) if gate is not None else 0,

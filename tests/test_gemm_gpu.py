@@ -148,57 +148,3 @@ def test_gemm_tile_modes_bitwise_equal(force_tile, pair, bn):
     force_tile(pair, bn)
     out = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS_GELU)
     assert torch.equal(out, base)
-
-
-# ------------------------------------------------------------------------------------------- stream-K
-def _sk_case(ops, M, N, K, epi, seed):
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    a = bf(torch.randn(M, K, generator=g)).to(DEV)
-    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
-    b = bf(torch.randn(N, generator=g)).to(DEV)
-    x = bf(torch.randn(M, N, generator=g)).to(DEV)
-    gate = bf(torch.randn(3, N, generator=g)).to(DEV)
-    kw = {"bias": dict(), "gelu": dict(epilogue=ops.EPI_BIAS_GELU), "res": dict(epilogue=ops.EPI_BIAS_RES, res=x),
-          "gate_res": dict(epilogue=ops.EPI_BIAS_GATE_RES, gate=gate, rows_per_gate=(M + 2) // 3, res=x)}[epi]
-    return a, w, b, kw
-
-
-@pytest.mark.parametrize("pair,bn", TILE_MODES)
-@pytest.mark.parametrize("M,N,K,epi", [(4680, 1536, 1536, "gate_res"), (4680, 1536, 8960, "gate_res"), (4680, 4608, 1536, "bias"),
-                                       (4680, 1536, 1536, "res"), (4680, 8960, 1536, "gelu"), (2340, 1536, 1536, "bias")])
-def test_gemm_stream_k(monkeypatch, pair, bn, M, N, K, epi):
-    """Stream-K mode (LLB_GEMM_TILE third field): every worker takes a contiguous range of (tile, k-block) units; tiles cut
-    between two workers are completed through the fp32 workspace.  Same result as the classic schedule up to the fp32
-    summation order inside the cut tiles (one extra partial sum before the bf16 rounding), rows past M untouched, and a
-    second launch on the same workspace (flags consumed by their readers) gives the same bits."""
-    ops = _ops()
-    a, w, b, kw = _sk_case(ops, M, N, K, epi, M + N + K)
-    monkeypatch.setenv("LLB_GEMM_TILE", f"{pair},{bn}")
-    base = ops.gemm(a, w, b, **{k: (v.clone() if k == "res" else v) for k, v in kw.items()})
-    monkeypatch.setenv("LLB_GEMM_TILE", f"{pair},{bn},1")
-    guard = torch.full((M + 4, N), 7.0, dtype=torch.bfloat16, device=DEV)
-    out = ops.gemm(a, w, b, out=guard[:M], **kw)
-    out2 = ops.gemm(a, w, b, **kw)
-    torch.cuda.synchronize()
-    assert (guard[M:] == 7.0).all()
-    assert torch.equal(out, out2), "second stream-K launch on the same workspace differs"
-    err = rel_l2(out, base)
-    frac = (out != base).float().mean().item()
-    assert err < 2e-3 and frac < 0.02, f"pair={pair} bn={bn}: rel-L2 vs classic {err}, {frac:.4f} of the outputs differ"
-    ref = a.float() @ w.float().t() + b.float()
-    if epi == "bias":
-        assert rel_l2(out, ref) < 4e-3
-
-
-def test_gemm_stream_k_is_chosen_for_the_block_shapes(monkeypatch):
-    """Without overrides the library picks stream-K for the N = 1536 projections at M = 4680 (and only when a workspace is
-    registered); LLB_GEMM_STREAMK is read once per process, so this only checks results, against the classic single tiles."""
-    ops = _ops()
-    monkeypatch.delenv("LLB_GEMM_TILE", raising=False)
-    for (M, N, K, epi) in [(4680, 1536, 1536, "gate_res"), (4680, 1536, 8960, "gate_res"), (18720, 1536, 1536, "res")]:
-        a, w, b, kw = _sk_case(ops, M, N, K, epi, 7 + K)
-        auto = ops.gemm(a, w, b, **kw)
-        monkeypatch.setenv("LLB_GEMM_TILE", "0,192")
-        base = ops.gemm(a, w, b, **kw)
-        monkeypatch.delenv("LLB_GEMM_TILE", raising=False)
-        assert rel_l2(auto, base) < 2e-3
