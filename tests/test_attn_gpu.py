@@ -122,3 +122,24 @@ def test_attention_outlier_keys(variant, rows):
     assert torch.isfinite(out.float()).all()
     err = rel_l2(out, ref)
     assert err < 1e-2, f"variant {variant}: rel-L2 {err}"
+
+
+@pytest.mark.parametrize("variant", **VARIANTS)
+@pytest.mark.parametrize("Lq,rows", [(72, 512), (200, 300), (4680, 512), (333, 2048)])
+def test_attention_output_view_and_guards(variant, Lq, rows):
+    """The output goes through shared memory and a TMA store whose tensor map carries the row stride and clips rows beyond
+    Lq: write into a column slice of a wider, longer buffer and check that nothing outside [0, Lq) x [c0, c0 + H*128) moves."""
+    ops = _ops()
+    H = 2
+    g = torch.Generator(device="cpu").manual_seed(Lq * 7 + rows)
+    q = bf(torch.randn(Lq, H * 128, generator=g)).to(DEV)
+    k = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    v = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=[(0, rows)]), DEV)
+    big = torch.full((Lq + 130, H * 128 + 128), 3.0, dtype=torch.bfloat16, device=DEV)
+    out = big[:Lq, 64:64 + H * 128]
+    ops.attention(q, k, v, sp, n_heads=H, out=out, variant=variant)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, H, [(0, rows)])
+    assert rel_l2(out, ref) < 8e-3
+    assert (big[Lq:] == 3.0).all() and (big[:, :64] == 3.0).all() and (big[:, 64 + H * 128:] == 3.0).all()
