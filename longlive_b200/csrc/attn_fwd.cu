@@ -49,17 +49,6 @@
 
 namespace llb {
 
-#ifdef LLB_ATTN_MCAST_EXPERIMENT
-__device__ __forceinline__ void umma_commit_kvempty(uint32_t bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(static_cast<uint16_t>(3))
-      : "memory");
-}
-#else
-__device__ __forceinline__ void umma_commit_kvempty(uint32_t bar) { umma_commit(bar); }
-#endif
-
 // LLB_ATTN_TRACE (debug builds only, tools/attn_trace.py): CTA 0 records clock64() at the hand-over points of the first
 // 64 key tiles of its first item: g_attn_trace[role][tile][slot], role 0 / 1 = softmax chain 0 / 1, 2 = the MMA issuer.
 #ifdef LLB_ATTN_TRACE
@@ -305,11 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(kvfull_bar(s), 1);
-#ifdef LLB_ATTN_MCAST_EXPERIMENT
-      mbar_init(kvempty_bar(s), 2);  // own MMA warp + the peer's (its multicast loads write this CTA's stage too)
-#else
       mbar_init(kvempty_bar(s), 1);
-#endif
     }
     fence_barrier_init();
   }
@@ -318,11 +303,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tmem_relinquish();
   }
   tc_fence_before();
-#ifdef LLB_ATTN_MCAST_EXPERIMENT
-  cluster_sync_all();
-#else
   __syncthreads();
-#endif
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // programmatic dependent launch (see llb_common.cuh): the setup above may overlap the previous
@@ -371,28 +352,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           auto load_tile = [&](const CUtensorMap* tm, int row0) {
             mbar_wait(kvempty_bar(stage), phase ^ 1);
             const uint32_t dst = kv_base + stage * kTileBytes;
-#ifdef LLB_ATTN_MCAST_EXPERIMENT  // timing / power experiment: each CTA of a cluster of two loads one 64-column box of the
-            // tile and multicasts it to both (valid only while both CTAs work on the same head and key range)
-            {
-              const uint32_t rk = cluster_ctarank();
-              mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
-              asm volatile(
-                  "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-                  " [%0], [%1, {%3, %4}], [%2], %5;"
-                  :
-                  : "r"(dst + rk * kBoxBytes), "l"(reinterpret_cast<uint64_t>(tm)), "r"(kvfull_bar(stage)),
-                    "r"(col + static_cast<int>(rk) * 64), "r"(row0), "h"(static_cast<uint16_t>(3))
-                  : "memory");
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-              return;
-            }
-#endif
-#ifdef LLB_ATTN_HALFLOAD_EXPERIMENT  // timing / power experiment only (garbage results): half the L2 -> SM K/V traffic
-            mbar_arrive_expect_tx(kvfull_bar(stage), kBoxBytes);
-            tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            return;
-#endif
             mbar_arrive_expect_tx(kvfull_bar(stage), kTileBytes);
             tma_load_2d(dst, tm, kvfull_bar(stage), col, row0);
             tma_load_2d(dst + kBoxBytes, tm, kvfull_bar(stage), col + 64, row0);
@@ -471,7 +430,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             umma_commit(sfull_bar(1));
             if (nt == 1) umma_commit(qempty_bar(1));
           }
-          umma_commit_kvempty(kvempty_bar(stage));
+          umma_commit(kvempty_bar(stage));
         }
         __syncwarp();
         advance();
@@ -517,8 +476,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               if (last_qk) umma_commit(qempty_bar(0));
             }
             if (!has1) {
-              umma_commit_kvempty(kvempty_bar(vstage));
-              if (more) umma_commit_kvempty(kvempty_bar(kstage));
+              umma_commit(kvempty_bar(vstage));
+              if (more) umma_commit(kvempty_bar(kstage));
             }
           }
           __syncwarp();
@@ -531,12 +490,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             if (elect_one()) {
               issue_pv(1, vst, j == 0);
               umma_commit(odone_bar(1));
-              umma_commit_kvempty(kvempty_bar(vstage));
+              umma_commit(kvempty_bar(vstage));
               if (more) {
                 issue_qk(1, kst);
                 umma_commit(sfull_bar(1));
                 if (last_qk) umma_commit(qempty_bar(1));
-                umma_commit_kvempty(kvempty_bar(kstage));
+                umma_commit(kvempty_bar(kstage));
               }
             }
             __syncwarp();
@@ -819,11 +778,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   tc_fence_before();
-#ifdef LLB_ATTN_MCAST_EXPERIMENT
-  cluster_sync_all();
-#else
   __syncthreads();
-#endif
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -841,18 +796,9 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = kAttnSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   unsigned n_attr = 0;
-#ifdef LLB_ATTN_MCAST_EXPERIMENT
-  attr[n_attr].id = cudaLaunchAttributeClusterDimension;
-  attr[n_attr].val.clusterDim.x = 2;
-  attr[n_attr].val.clusterDim.y = 1;
-  attr[n_attr].val.clusterDim.z = 1;
-  ++n_attr;
-  static const bool coop = false;
-#else
   static const bool coop = getenv("LLB_ATTN_COOP") == nullptr || atoi(getenv("LLB_ATTN_COOP")) != 0;
-#endif
   if (coop) {
     attr[n_attr].id = cudaLaunchAttributeCooperative;
     attr[n_attr].val.cooperative = 1;
