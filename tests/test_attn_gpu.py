@@ -143,3 +143,25 @@ def test_attention_output_view_and_guards(variant, Lq, rows):
     ref = _attn_ref(q, k, v, H, [(0, rows)])
     assert rel_l2(out, ref) < 8e-3
     assert (big[Lq:] == 3.0).all() and (big[:, :64] == 3.0).all() and (big[:, 64 + H * 128:] == 3.0).all()
+
+
+@pytest.mark.parametrize("variant", **VARIANTS)
+@pytest.mark.parametrize("Lq,H,rows,segs", [
+    (1, 1, 1, [(0, 1)]),                                   # one query, one key: softmax of a single logit
+    (1, 3, 700, [(699, 1)]),                               # the last row of the cache only
+    (129, 2, 1024, [(0, 129)]),                            # a full tile + a one-key tile, a full Q tile + a one-row Q tile
+    (300, 1, 2048, [(0, 128), (500, 0), (700, 1)]),        # an empty range between two others
+    (257, 2, 4096, [(3, 61), (1000, 128), (2047, 2), (3000, 1096)]),  # four ranges (LLB_MAX_SEGS), unaligned starts
+])
+def test_attention_edge_shapes(variant, Lq, H, rows, segs):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(Lq * 31 + rows)
+    q = bf(torch.randn(Lq, H * 128, generator=g)).to(DEV)
+    k = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    v = bf(torch.randn(rows, H * 128, generator=g)).to(DEV)
+    sp = ops.step_params_tensor(ops.make_step_params(attn_segs=segs), DEV)
+    out = ops.attention(q, k, v, sp, n_heads=H, variant=variant)
+    ref = _attn_ref(q, k, v, H, [s for s in segs if s[1] > 0])
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 8e-3
