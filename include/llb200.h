@@ -196,9 +196,10 @@ int llb_quant_rows_fp8(const void* x, int64_t ldx, void* out8, int64_t ld8, floa
  *   q   [Lq, n_heads*128] bf16, k/v [kv_rows, n_heads*128] bf16, out [Lq, n_heads*128] bf16.
  *   The attended keys are the union of physical row ranges listed in seg_dev
  *   (llb_step_params.n_attn_segs / attn_start / attn_len, device memory).
- *   variant: 0 = default; measured alternatives kept for comparison (same results): bit 0 P through
- *   shared memory, bit 1 MUFU-only exp2, bit 2 P handed over in two halves, bit 3 half-tile (64-key) pipeline,
- *   bit 4 two softmax warpgroups per Q tile.
+ *   out must be 16-byte aligned with ldo a multiple of 8 (single-GPU launches store it with TMA: rows >= Lq and
+ *   columns outside [0, n_heads*128) of a wider buffer are never touched).
+ *   variant: 0 = default (single-CTA kernel); 64 = the CTA-pair cta_group::2 kernel (same results, measured slower,
+ *   DESIGN.md 4.1).  The other variants of rounds 1-2 were measured and removed (profiles/r02_attn_*.md).
  * ------------------------------------------------------------------------------------------ */
 int llb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                  int64_t ldv, void* out, int64_t ldo, int Lq, int n_heads, int kv_rows,
